@@ -1,0 +1,172 @@
+// epi_abi.cu — the extern "C" boundary declared in include/epipolar_b200.h.
+// Validates arguments, carves the caller's workspace, launches kernels on the caller's stream.
+#include <cstdio>
+#include <cstring>
+
+#include "../../include/epipolar_b200.h"
+#include "epi_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+thread_local int g_launches = 0;
+
+int fail(int code, const char *fmt, const char *detail = "") {
+    snprintf(g_err, sizeof(g_err), fmt, detail);
+    return code;
+}
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+bool src_is_channels_last(const EpiFusionParams *p) {
+    const int64_t *s = p->src_stride;
+    const int64_t C = p->C, H = p->H, W = p->W;
+    return s[1] == 1 && s[3] == C && s[2] == W * C && (p->N == 1 || s[0] == H * W * C) &&
+           (reinterpret_cast<uintptr_t>(p->feat_src) % 16 == 0);
+}
+
+struct Plan {
+    size_t off_src = 0, off_prez = 0, total = 0;
+    bool stage_src = false, has_z = false;
+};
+
+Plan make_plan(const EpiFusionParams *p) {
+    Plan pl;
+    const size_t map = (size_t)p->N * p->C * p->H * p->W * sizeof(float);
+    pl.stage_src = !src_is_channels_last(p);
+    pl.has_z = p->z_weight_folded != nullptr;
+    size_t off = 0;
+    if (pl.stage_src) { pl.off_src = off; off += align_up(map); }
+    if (pl.has_z) { pl.off_prez = off; off += align_up(map); }
+    pl.total = off;
+    return pl;
+}
+
+int validate(const EpiFusionParams *p) {
+    if (!p) return fail(EPI_EINVAL, "params is null");
+    if (!p->feat_ref || !p->feat_src || !p->out) return fail(EPI_EINVAL, "feat_ref/feat_src/out must be non-null");
+    if (!p->sample_locs_in && (!p->P_ref || !p->P_src)) return fail(EPI_EINVAL, "P_ref/P_src required without sample_locs_in");
+    if (p->N <= 0 || p->C <= 0 || p->H < 2 || p->W < 2) return fail(EPI_EINVAL, "need N,C >= 1 and H,W >= 2");
+    if (p->K < 2 || p->K > 256) return fail(EPI_EINVAL, "K (SAMPLESIZE) must be in [2,256]");
+    if (p->C > 1024 || (p->C > 512 && p->C % 4 != 0)) return fail(EPI_EINVAL, "C must be <= 512, or <= 1024 and a multiple of 4");
+    if (!(p->downsample > 0.f) || !(p->img_scale > 0.f)) return fail(EPI_EINVAL, "downsample and img_scale must be positive");
+    if (p->z_weight_folded && !p->z_bias_folded) return fail(EPI_EINVAL, "z_bias_folded required with z_weight_folded");
+    if (p->variant < EPI_VARIANT_AUTO || p->variant > EPI_VARIANT_TILE) return fail(EPI_EINVAL, "unknown variant");
+    return EPI_OK;
+}
+
+epi::GeomCfg make_geom(int H, int W, int K, float ds, float r, float eps, int correct, int align) {
+    epi::GeomCfg g;
+    g.ds = ds; g.r = r; g.eps = eps;
+    g.xmin = epi::pix2coord(0, ds, r); g.xmax = epi::pix2coord(W - 1, ds, r);
+    g.ymin = epi::pix2coord(0, ds, r); g.ymax = epi::pix2coord(H - 1, ds, r);
+    g.correct = correct; g.align = align; g.H = H; g.W = W; g.K = K;
+    return g;
+}
+
+}  // namespace
+
+extern "C" {
+
+int epi_version(void) { return EPI_ABI_VERSION; }
+
+const char *epi_last_error(void) { return g_err; }
+
+int epi_last_launch_count(void) { return g_launches; }
+
+size_t epi_fusion_workspace_bytes(const EpiFusionParams *p) {
+    if (!p || p->N <= 0 || p->C <= 0 || p->H <= 0 || p->W <= 0) return 0;
+    return make_plan(p).total;
+}
+
+int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
+    int rc = validate(p);
+    if (rc != EPI_OK) return rc;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const Plan pl = make_plan(p);
+    if (pl.total > 0 && (!p->workspace || p->workspace_bytes < pl.total)) return fail(EPI_EWORKSPACE, "workspace too small");
+    if (pl.total > 0 && reinterpret_cast<uintptr_t>(p->workspace) % 256 != 0) return fail(EPI_EINVAL, "workspace must be 256-byte aligned");
+    char *ws = static_cast<char *>(p->workspace);
+    int launches = 0;
+    cudaError_t e;
+
+    epi::FusionArgs a;
+    memset(&a, 0, sizeof(a));
+    a.feat_ref = p->feat_ref;
+    a.P_ref = p->P_ref; a.P_src = p->P_src; a.locs_in = p->sample_locs_in;
+    a.attn = p->attn; a.corr_pos = p->corr_pos; a.locs_out = p->sample_locs_out;
+    a.N = p->N; a.C = p->C; a.softmax_scale = p->softmax_scale;
+    for (int i = 0; i < 4; i++) a.ref_stride[i] = p->ref_stride[i];
+    a.geom = make_geom(p->H, p->W, p->K, p->downsample, p->img_scale, p->eps, p->correct_normalize, p->align_corners);
+
+    if (pl.stage_src) {
+        float *nhwc = reinterpret_cast<float *>(ws + pl.off_src);
+        e = epi::launch_nchw_to_nhwc(p->feat_src, p->src_stride, nhwc, p->N, p->C, p->H, p->W, st);
+        if (e != cudaSuccess) return fail(EPI_ECUDA, "layout staging launch failed: %s", cudaGetErrorString(e));
+        launches++;
+        a.src_nhwc = nhwc;
+    } else {
+        a.src_nhwc = p->feat_src;
+    }
+
+    if (pl.has_z) {     // fused feature goes to the pre-z buffer (contiguous NCHW), epilogue writes `out`
+        a.out = reinterpret_cast<float *>(ws + pl.off_prez);
+        a.out_stride[0] = (int64_t)p->C * p->H * p->W; a.out_stride[1] = (int64_t)p->H * p->W;
+        a.out_stride[2] = p->W; a.out_stride[3] = 1;
+        a.add_ref = 0;
+    } else {
+        a.out = p->out;
+        for (int i = 0; i < 4; i++) a.out_stride[i] = p->out_stride[i];
+        a.add_ref = p->add_ref_residual;
+    }
+
+    bool use_tile = false;
+    if (p->variant == EPI_VARIANT_TILE) {
+        if (!epi::fusion_tile_supported(a)) return fail(EPI_EINVAL, "tile variant does not support this shape");
+        use_tile = true;
+    } else if (p->variant == EPI_VARIANT_AUTO) {
+        use_tile = epi::fusion_tile_supported(a);
+    }
+    e = use_tile ? epi::launch_fusion_tile(a, st) : epi::launch_fusion_warp(a, st);
+    if (e != cudaSuccess) return fail(EPI_ECUDA, "fusion kernel launch failed: %s", cudaGetErrorString(e));
+    launches++;
+
+    if (pl.has_z) {
+        epi::ZArgs z;
+        memset(&z, 0, sizeof(z));
+        z.x = a.out;
+        for (int i = 0; i < 4; i++) { z.x_stride[i] = a.out_stride[i]; z.y_stride[i] = p->out_stride[i]; z.ref_stride[i] = p->ref_stride[i]; }
+        z.ref = p->feat_ref; z.y = p->out; z.Wf = p->z_weight_folded; z.bf = p->z_bias_folded;
+        z.N = p->N; z.C = p->C; z.HW = p->H * p->W; z.W = p->W;
+        z.z_residual = p->z_residual; z.add_ref = p->add_ref_residual;
+        e = epi::launch_z_epilogue(z, st);
+        if (e != cudaSuccess) return fail(EPI_ECUDA, "z epilogue launch failed: %s", cudaGetErrorString(e));
+        launches++;
+    }
+    g_launches = launches;
+    return EPI_OK;
+}
+
+int epi_sample_locs_f32(const float *P_ref, const float *P_src, float *sample_locs_out, int32_t N, int32_t H,
+                        int32_t W, int32_t K, float downsample, float img_scale, float eps,
+                        int32_t correct_normalize, void *stream) {
+    if (!P_ref || !P_src || !sample_locs_out) return fail(EPI_EINVAL, "null pointer");
+    if (N <= 0 || H < 2 || W < 2 || K < 2) return fail(EPI_EINVAL, "bad shape");
+    epi::GeomCfg g = make_geom(H, W, K, downsample, img_scale, eps, correct_normalize, 0);
+    cudaError_t e = epi::launch_sample_locs(P_ref, P_src, sample_locs_out, N, g, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(EPI_ECUDA, "sample_locs launch failed: %s", cudaGetErrorString(e));
+    return EPI_OK;
+}
+
+int epi_fold_z_bn_f32(const float *z_weight, const float *z_bias, const float *bn_weight, const float *bn_bias,
+                      const float *bn_mean, const float *bn_var, float bn_eps, int32_t C, float *w_folded,
+                      float *b_folded, void *stream) {
+    if (!z_weight || !bn_weight || !bn_bias || !bn_mean || !bn_var || !w_folded || !b_folded || C <= 0)
+        return fail(EPI_EINVAL, "null pointer or bad C");
+    cudaError_t e = epi::launch_fold_z_bn(z_weight, z_bias, bn_weight, bn_bias, bn_mean, bn_var, bn_eps, C, w_folded,
+                                          b_folded, reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(EPI_ECUDA, "fold launch failed: %s", cudaGetErrorString(e));
+    return EPI_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,151 @@
+// epi_aux.cu — layout staging, parameter folding, the z/BN epilogue and the geometry-only kernel.
+#include "epi_kernels.cuh"
+
+namespace epi {
+
+// ------------------------------------------------------------------------------------------
+// [N,C,H,W] (any strides) -> [N,H,W,C] contiguous.  32x32 shared-memory transpose per item:
+// reads are coalesced along the pixel axis when stride[3]==1 (NCHW), writes along channels.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) nchw_to_nhwc_kernel(const float *__restrict__ src, int64_t sn, int64_t sc,
+                                                           int64_t sh, int64_t sw, float *__restrict__ dst,
+                                                           int C, int H, int W) {
+    __shared__ float tile[32][33];
+    const int HW = H * W;
+    const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;          // 32 x 8
+    const float *s = src + (int64_t)n * sn;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int c = c0 + ty + i * 8, p = p0 + tx;
+        tile[ty + i * 8][tx] = (c < C && p < HW) ? __ldg(s + c * sc + (p / W) * sh + (p % W) * sw) : 0.f;
+    }
+    __syncthreads();
+    float *d = dst + (size_t)n * HW * C;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int p = p0 + ty + i * 8, c = c0 + tx;
+        if (c < C && p < HW) d[(size_t)p * C + c] = tile[tx][ty + i * 8];
+    }
+}
+
+cudaError_t launch_nchw_to_nhwc(const float *src, const int64_t stride[4], float *dst, int N, int C, int H, int W,
+                                cudaStream_t st) {
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32, N);
+    nchw_to_nhwc_kernel<<<grid, 256, 0, st>>>(src, stride[0], stride[1], stride[2], stride[3], dst, C, H, W);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// Fold conv1x1 z + eval BN (epipolar.py:250-251, BN.py:79 with training=False) into Wf, bf.
+// ------------------------------------------------------------------------------------------
+__global__ void fold_z_bn_kernel(const float *__restrict__ zw, const float *__restrict__ zb,
+                                 const float *__restrict__ g, const float *__restrict__ b,
+                                 const float *__restrict__ mean, const float *__restrict__ var, float eps, int C,
+                                 float *__restrict__ wf, float *__restrict__ bf) {
+    const int o = blockIdx.x;
+    const float s = g[o] / sqrtf(var[o] + eps);
+    for (int c = threadIdx.x; c < C; c += blockDim.x) wf[(size_t)o * C + c] = s * zw[(size_t)o * C + c];
+    if (threadIdx.x == 0) bf[o] = s * ((zb ? zb[o] : 0.f) - mean[o]) + b[o];
+}
+
+cudaError_t launch_fold_z_bn(const float *zw, const float *zb, const float *g, const float *b, const float *mean,
+                             const float *var, float eps, int C, float *wf, float *bf, cudaStream_t st) {
+    fold_z_bn_kernel<<<C, 128, 0, st>>>(zw, zb, g, b, mean, var, eps, C, wf, bf);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// z epilogue: per item Y[C x HW] = Wf[C x C] · X[C x HW] + bf (+X) (+ref).  fp32 CUDA-core
+// SGEMM, 64x64 tile, 4x4 per thread.  X is the library's own contiguous pre-z buffer.
+// ------------------------------------------------------------------------------------------
+constexpr int ZT = 64, ZK = 16;
+
+__global__ void __launch_bounds__(256) z_epilogue_kernel(const ZArgs z) {
+    __shared__ float Ws[ZK][ZT + 1];     // [k][o]
+    __shared__ float Xs[ZK][ZT + 1];     // [k][p]
+    const int n = blockIdx.z, o0 = blockIdx.y * ZT, p0 = blockIdx.x * ZT;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;       // tx -> p, ty -> o
+    const int C = z.C, HW = z.HW, W = z.W;
+    const float *X = z.x + (int64_t)n * z.x_stride[0];
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < C; k0 += ZK) {
+        for (int idx = tid; idx < ZK * ZT; idx += 256) {
+            int kk = idx & (ZK - 1), oo = idx / ZK;                   // W rows are contiguous in c
+            int o = o0 + oo, c = k0 + kk;
+            Ws[kk][oo] = (o < C && c < C) ? __ldg(z.Wf + (size_t)o * C + c) : 0.f;
+            int pp = idx & (ZT - 1), kx = idx / ZT;
+            int p = p0 + pp, cx = k0 + kx;
+            Xs[kx][pp] = (p < HW && cx < C) ? __ldg(X + cx * z.x_stride[1] + (p / W) * z.x_stride[2] + (p % W) * z.x_stride[3]) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < ZK; kk++) {
+            float wv[4], xv[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { wv[i] = Ws[kk][ty * 4 + i]; xv[i] = Xs[kk][tx + 16 * i]; }
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[i][j] = fmaf(wv[i], xv[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float *Y = z.y + (int64_t)n * z.y_stride[0];
+    const float *R = z.ref ? z.ref + (int64_t)n * z.ref_stride[0] : nullptr;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int o = o0 + ty * 4 + i;
+        if (o >= C) continue;
+        float b = __ldg(z.bf + o);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            int p = p0 + tx + 16 * j;
+            if (p >= HW) continue;
+            int yy = p / W, xx = p % W;
+            float v = acc[i][j] + b;
+            if (z.z_residual) v += __ldg(X + o * z.x_stride[1] + yy * z.x_stride[2] + xx * z.x_stride[3]);
+            if (z.add_ref && R) v += __ldg(R + o * z.ref_stride[1] + yy * z.ref_stride[2] + xx * z.ref_stride[3]);
+            Y[o * z.y_stride[1] + yy * z.y_stride[2] + xx * z.y_stride[3]] = v;
+        }
+    }
+}
+
+cudaError_t launch_z_epilogue(const ZArgs &z, cudaStream_t st) {
+    dim3 grid((z.HW + ZT - 1) / ZT, (z.C + ZT - 1) / ZT, z.N);
+    z_epilogue_kernel<<<grid, 256, 0, st>>>(z);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// geometry only: sample locations [K,N,H,W,2] (grid2sample_locs, epipolar.py:323-418)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sample_locs_kernel(const float *__restrict__ P_ref, const float *__restrict__ P_src,
+                                                          float *__restrict__ locs, int N, const GeomCfg gc) {
+    __shared__ PairGeom sg;
+    const int n = blockIdx.y, HW = gc.H * gc.W;
+    if (threadIdx.x == 0) pair_geom_from_krt(P_ref + 12 * n, P_src + 12 * n, sg);
+    __syncthreads();
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= HW) return;
+    float sx, sy, ex, ey;
+    line_endpoints(sg, gc, pix2coord(p % gc.W, gc.ds, gc.r), pix2coord(p / gc.W, gc.ds, gc.r), sx, sy, ex, ey);
+    for (int k = 0; k < gc.K; k++) {
+        float t = (float)k / (float)(gc.K - 1);
+        reinterpret_cast<float2 *>(locs)[((size_t)k * N + n) * HW + p] =
+            make_float2(img2grid(sx + (ex - sx) * t, gc, gc.W), img2grid(sy + (ey - sy) * t, gc, gc.H));
+    }
+}
+
+cudaError_t launch_sample_locs(const float *P_ref, const float *P_src, float *locs, int N, const GeomCfg &gc,
+                               cudaStream_t st) {
+    dim3 grid((gc.H * gc.W + 255) / 256, N);
+    sample_locs_kernel<<<grid, 256, 0, st>>>(P_ref, P_src, locs, N, gc);
+    return cudaGetLastError();
+}
+
+}  // namespace epi

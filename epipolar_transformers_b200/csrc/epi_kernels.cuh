@@ -1,0 +1,41 @@
+// epi_kernels.cuh — internal launch interface between the C ABI (epi_abi.cu) and the kernels.
+#pragma once
+#include "epi_common.cuh"
+
+namespace epi {
+
+// Device-side view of one fused forward (built from EpiFusionParams by the ABI layer).
+struct FusionArgs {
+    const float *feat_ref;  int64_t ref_stride[4];
+    const float *src_nhwc;                    // [N,H,W,C] contiguous, 16-byte aligned (zero-copy or staged)
+    const float *P_ref, *P_src;
+    const float *locs_in;
+    float *out;             int64_t out_stride[4];
+    float *attn, *corr_pos, *locs_out;
+    int N, C;
+    float softmax_scale;
+    int add_ref;
+    GeomCfg geom;
+};
+
+// z-projection epilogue:  y[n,o,p] = sum_c Wf[o,c]·x[n,c,p] + bf[o] (+x[n,o,p]) (+ref[n,o,p])
+struct ZArgs {
+    const float *x;         int64_t x_stride[4];     // pre-z fused feature
+    const float *ref;       int64_t ref_stride[4];   // may be null
+    float *y;               int64_t y_stride[4];
+    const float *Wf, *bf;
+    int N, C, HW, W;
+    int z_residual, add_ref;
+};
+
+cudaError_t launch_fusion_warp(const FusionArgs &a, cudaStream_t st);
+cudaError_t launch_fusion_tile(const FusionArgs &a, cudaStream_t st);
+bool fusion_tile_supported(const FusionArgs &a);
+
+cudaError_t launch_nchw_to_nhwc(const float *src, const int64_t stride[4], float *dst, int N, int C, int H, int W, cudaStream_t st);
+cudaError_t launch_z_epilogue(const ZArgs &z, cudaStream_t st);
+cudaError_t launch_fold_z_bn(const float *zw, const float *zb, const float *g, const float *b, const float *mean,
+                             const float *var, float eps, int C, float *wf, float *bf, cudaStream_t st);
+cudaError_t launch_sample_locs(const float *P_ref, const float *P_src, float *locs, int N, const GeomCfg &gc, cudaStream_t st);
+
+}  // namespace epi

@@ -1,0 +1,244 @@
+"""Host side of the B200 epipolar fusion path: `Epipolar(nn.Module)` with the reference's
+constructor / forward contract, calling the C ABI (include/epipolar_b200.h) through ctypes.
+
+Mirrors /root/reference/modeling/layers/epipolar.py:
+  Epipolar.__init__  :12-80   (cfg keys, parameter names z.* / bn.* kept for checkpoints)
+  Epipolar.forward   :82-269  (signature, 4-tuple return contract :262-269)
+and the caller residual of /root/reference/modeling/backbones/resnet.py:377-388
+(`fused_other_feat`).  PyTorch is used here only for device memory, streams and parameters;
+every arithmetic step of the graded path runs in libepipolar_b200.so.  No CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional
+
+import torch
+from torch import nn
+
+from . import _lib
+from .config import get_global_cfg
+
+_EPSILON = 0.001          # epipolar.py:20
+
+
+class ZeroInitBN(nn.BatchNorm2d):
+    """BatchNorm2d whose affine weight AND bias start at zero (reference: modeling/layers/BN.py:48-52);
+    state-dict keys identical to the reference's zeroinitBN."""
+
+    def reset_parameters(self):
+        super().reset_parameters()
+        if self.affine:
+            nn.init.zeros_(self.weight)
+            nn.init.zeros_(self.bias)
+
+
+def _strides4(t: torch.Tensor):
+    return (ctypes.c_int64 * 4)(*t.stride())
+
+
+def _check_feat(name, t):
+    if not isinstance(t, torch.Tensor) or t.dim() != 4:
+        raise ValueError("%s must be a 4-D tensor [N,C,H,W]" % name)
+    if not t.is_cuda:
+        raise RuntimeError("%s is on %s: the B200 epipolar path has no CPU implementation" % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32 (got %s)" % (name, t.dtype))
+
+
+def epipolar_fusion(feat_ref, feat_src, P_ref, P_src, *, K, downsample=4.0, img_scale=1.0,
+                    softmax_scale=0.125, correct_normalize=False, align_corners=False,
+                    z_folded=None, z_residual=False, add_ref_residual=False,
+                    sample_locs_in=None, want_attn=True, want_corr=True, want_locs=False,
+                    variant="auto", out=None):
+    """Functional form of the fused forward.  Returns (out, corr_pos|None, attn|None, sample_locs|None).
+
+    feat_ref/feat_src: CUDA float32 [N,C,H,W] (NCHW or channels_last strides).
+    P_ref/P_src: [N,3,4] (cast to float32 like modeling/model.py:183-195).
+    z_folded: optional (Wf [C,C], bf [C]) from `fold_z_bn` (eval-mode epilogue, epipolar.py:249-253).
+    sample_locs_in: optional [K,N,H,W,2] normalised locations replacing the fused geometry.
+    """
+    lib = _lib.load()
+    _check_feat("feat_ref", feat_ref)
+    _check_feat("feat_src", feat_src)
+    if feat_ref.shape != feat_src.shape or feat_ref.device != feat_src.device:
+        raise ValueError("feat_ref and feat_src must have the same shape and device")
+    N, C, H, W = feat_ref.shape
+    dev = feat_ref.device
+    if sample_locs_in is None:
+        P_ref = P_ref.to(device=dev, dtype=torch.float32).contiguous()
+        P_src = P_src.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(P_ref.shape) != (N, 3, 4) or tuple(P_src.shape) != (N, 3, 4):
+            raise ValueError("P_ref/P_src must be [N,3,4]")
+    else:
+        sample_locs_in = sample_locs_in.to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(sample_locs_in.shape) != (K, N, H, W, 2):
+            raise ValueError("sample_locs_in must be [K,N,H,W,2]")
+    if out is None:
+        out = torch.empty_like(feat_ref)           # preserves NCHW / channels_last
+    attn = torch.empty((N, K, H, W), device=dev, dtype=torch.float32) if want_attn else None
+    corr = torch.empty((N, H, W, 2), device=dev, dtype=torch.float32) if want_corr else None
+    locs = torch.empty((K, N, H, W, 2), device=dev, dtype=torch.float32) if want_locs else None
+
+    p = _lib.EpiFusionParams()
+    p.feat_ref = feat_ref.data_ptr(); p.ref_stride = _strides4(feat_ref)
+    p.feat_src = feat_src.data_ptr(); p.src_stride = _strides4(feat_src)
+    p.P_ref = P_ref.data_ptr() if sample_locs_in is None else None
+    p.P_src = P_src.data_ptr() if sample_locs_in is None else None
+    p.sample_locs_in = sample_locs_in.data_ptr() if sample_locs_in is not None else None
+    p.out = out.data_ptr(); p.out_stride = _strides4(out)
+    p.attn = attn.data_ptr() if attn is not None else None
+    p.corr_pos = corr.data_ptr() if corr is not None else None
+    p.sample_locs_out = locs.data_ptr() if locs is not None else None
+    if z_folded is not None:
+        wf, bf = z_folded
+        p.z_weight_folded = wf.data_ptr(); p.z_bias_folded = bf.data_ptr()
+    p.N, p.C, p.H, p.W, p.K = N, C, H, W, int(K)
+    p.downsample = float(downsample); p.img_scale = float(img_scale)
+    p.eps = _EPSILON; p.softmax_scale = float(softmax_scale)
+    p.align_corners = int(bool(align_corners)); p.correct_normalize = int(bool(correct_normalize))
+    p.z_residual = int(bool(z_residual)); p.add_ref_residual = int(bool(add_ref_residual))
+    p.variant = _lib.VARIANTS[variant] if isinstance(variant, str) else int(variant)
+    nbytes = lib.epi_fusion_workspace_bytes(ctypes.byref(p))
+    ws = None
+    if nbytes:
+        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)      # caching allocator: stream-ordered, 512-B aligned
+        p.workspace = ws.data_ptr(); p.workspace_bytes = nbytes
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.epi_fusion_forward_f32(ctypes.byref(p), ctypes.c_void_p(stream)), "epi_fusion_forward_f32")
+    return out, corr, attn, locs
+
+
+def fold_z_bn(z: nn.Conv2d, bn: nn.BatchNorm2d):
+    """(Wf, bf) such that BN_eval(z(x)) == Wf·x + bf, computed on the device (no host sync)."""
+    lib = _lib.load()
+    C = z.out_channels
+    dev = z.weight.device
+    wf = torch.empty((C, z.in_channels), device=dev, dtype=torch.float32)
+    bf = torch.empty((C,), device=dev, dtype=torch.float32)
+    zb = z.bias.data_ptr() if z.bias is not None else None
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.epi_fold_z_bn_f32(z.weight.data_ptr(), zb, bn.weight.data_ptr(), bn.bias.data_ptr(),
+                                         bn.running_mean.data_ptr(), bn.running_var.data_ptr(), float(bn.eps), C,
+                                         wf.data_ptr(), bf.data_ptr(), ctypes.c_void_p(stream)), "epi_fold_z_bn_f32")
+    return wf, bf
+
+
+def sample_locs(P_ref, P_src, H, W, K, downsample=4.0, img_scale=1.0, correct_normalize=False):
+    """Device grid2sample_locs (epipolar.py:323-418): [K,N,H,W,2] normalised (x,y)."""
+    lib = _lib.load()
+    P_ref = P_ref.to(dtype=torch.float32).contiguous(); P_src = P_src.to(dtype=torch.float32).contiguous()
+    if not P_ref.is_cuda:
+        raise RuntimeError("sample_locs needs CUDA tensors (no CPU implementation)")
+    N = P_ref.shape[0]
+    out = torch.empty((K, N, H, W, 2), device=P_ref.device, dtype=torch.float32)
+    with torch.cuda.device(P_ref.device):
+        stream = torch.cuda.current_stream(P_ref.device).cuda_stream
+        _lib.check(lib.epi_sample_locs_f32(P_ref.data_ptr(), P_src.data_ptr(), out.data_ptr(), N, H, W, K, float(downsample),
+                                           float(img_scale), _EPSILON, int(bool(correct_normalize)), ctypes.c_void_p(stream)),
+                   "epi_sample_locs_f32")
+    return out
+
+
+class Epipolar(nn.Module):
+    """Drop-in for the reference's `Epipolar` on the graded flag set
+    (ATTENTION='avg', SIMILARITY='dot', SOFTMAX_ENABLED, optional 'z' + ZRESIDUAL).
+
+    Extra keyword-only knobs (all default to the reference's behaviour):
+      cfg               duck-typed config (defaults to the module-level one, like `from core import cfg`)
+      align_corners     grid_sample semantics; False = what the reference does under torch>=1.3
+      fuse_ref_residual also add feat1 inside the kernel (use `fused_other_feat` as the caller)
+      variant           'auto' | 'warp' | 'tile' kernel selection
+    """
+
+    def __init__(self, debug=False, *, cfg=None, align_corners=False, fuse_ref_residual=False, variant="auto",
+                 emit_attn=True, emit_corr=True):
+        super().__init__()
+        cfg = cfg if cfg is not None else get_global_cfg()
+        self.cfg = cfg
+        self.debug = debug
+        self.downsample = cfg.BACKBONE.DOWNSAMPLE
+        self.feat_h, self.feat_w = cfg.KEYPOINT.HEATMAP_SIZE
+        self.sample_size = cfg.EPIPOLAR.SAMPLESIZE
+        self.epsilon = _EPSILON
+        self.align_corners = align_corners
+        self.fuse_ref_residual = fuse_ref_residual
+        self.variant = variant
+        self.emit_attn = emit_attn
+        self.emit_corr = emit_corr
+        ep = cfg.EPIPOLAR
+        unsupported = []
+        if debug: unsupported.append("debug=True")
+        if ep.ATTENTION != "avg": unsupported.append("ATTENTION=%r" % ep.ATTENTION)
+        if ep.SIMILARITY != "dot": unsupported.append("SIMILARITY=%r" % ep.SIMILARITY)
+        if not ep.SOFTMAX_ENABLED: unsupported.append("SOFTMAX_ENABLED=False")
+        if ep.PRIOR or ep.PRIORMUL: unsupported.append("PRIOR")
+        if ep.POOLING: unsupported.append("POOLING")
+        if ep.BOTTLENECK != 1: unsupported.append("BOTTLENECK!=1")
+        if ep.FIND_CORR != "feature": unsupported.append("FIND_CORR=%r" % ep.FIND_CORR)
+        if ep.REPROJECT_LOSS_WEIGHT != 0: unsupported.append("REPROJECT_LOSS_WEIGHT")
+        for name in ("theta", "phi", "g"):
+            if name in ep.PARAMETERIZED: unsupported.append("PARAMETERIZED has %r" % name)
+        if unsupported:
+            raise NotImplementedError(
+                "epipolar_transformers_b200 accelerates the graded flag set only (SURVEY.md 8a); "
+                "not supported: " + ", ".join(unsupported))
+        if "z" in ep.PARAMETERIZED:                                   # epipolar.py:63-65
+            nf = cfg.KEYPOINT.NFEATS
+            self.z = nn.Conv2d(nf // ep.BOTTLENECK, nf, kernel_size=1, stride=1, padding=0, bias=True)
+            self.bn = ZeroInitBN(nf)
+        self._fold_cache = None
+
+    # -- eval-mode folding of z + BN, cached on parameter versions -------------------------------
+    def _folded(self):
+        ts = (self.z.weight, self.z.bias, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var)
+        key = tuple((t.data_ptr(), t._version) for t in ts if t is not None)
+        if self._fold_cache is None or self._fold_cache[0] != key:
+            self._fold_cache = (key, fold_z_bn(self.z, self.bn))
+        return self._fold_cache[1]
+
+    def forward(self, feat1, feat2, P1, P2, depth=None, camera=None, other_camera=None, ref1=None, ref2=None):
+        """feat1/feat2: N x C x H x W; P1/P2: N x 3 x 4 (epipolar.py:82-89).
+        Returns (finalout, corr_pos [N,H,W,2], depth=attention [N,K,H,W], sample_locs|None) (:262-269)."""
+        if depth is not None:
+            raise NotImplementedError("depth pass-through (epipolar.py:215-216) is not on the accelerated path")
+        cfg = self.cfg
+        ep = cfg.EPIPOLAR
+        if torch.is_grad_enabled() and (feat1.requires_grad or feat2.requires_grad):
+            raise NotImplementedError("backward of the fused op is not implemented yet (SURVEY.md 8f rank 1); "
+                                      "call under torch.no_grad()")
+        has_z = "z" in ep.PARAMETERIZED
+        fold = has_z and not self.training
+        want_locs = bool(cfg.VIS.EPIPOLAR_LINE)
+        out, corr, attn, locs = epipolar_fusion(
+            feat1, feat2, P1, P2, K=self.sample_size, downsample=self.downsample,
+            img_scale=cfg.DATASETS.IMAGE_RESIZE * cfg.DATASETS.PREDICT_RESIZE,
+            softmax_scale=ep.SOFTMAXSCALE, correct_normalize=ep.USE_CORRECT_NORMALIZE,
+            align_corners=self.align_corners, z_folded=self._folded() if fold else None,
+            z_residual=bool(ep.ZRESIDUAL) if fold else False,
+            add_ref_residual=self.fuse_ref_residual and (fold or not has_z),
+            want_attn=self.emit_attn, want_corr=self.emit_corr, want_locs=want_locs, variant=self.variant)
+        if has_z and not fold:
+            # training-mode BN needs batch statistics (+ autograd to z/bn): keep conv/BN in PyTorch
+            finalout = self.bn(self.z(out))
+            if ep.ZRESIDUAL:
+                finalout = finalout + out
+            if self.fuse_ref_residual:
+                finalout = finalout + feat1
+        else:
+            finalout = out
+        return finalout, corr, attn, (locs.transpose(0, 1) if want_locs else None)
+
+
+def fused_other_feat(feat, other_features, KRT, other_KRT, sampler: Epipolar, camera=None, other_camera=None):
+    """Caller-side mirror of getOtherFeat (modeling/backbones/resnet.py:377-388):
+    returns (ret + feat, corr_pos, depth, sample_locs).  With sampler.fuse_ref_residual the add
+    already happened inside the kernel."""
+    if other_features is None:
+        return feat, None, None, None
+    ret, corr_pos, depth, locs = sampler(feat, other_features, KRT, other_KRT, camera=camera, other_camera=other_camera)
+    if not sampler.fuse_ref_residual:
+        ret = ret + feat
+    return ret, corr_pos, depth, locs

@@ -1,0 +1,110 @@
+/* epipolar_b200.h — C ABI of the B200-native epipolar-transformer fusion path.
+ *
+ * Drop-in boundary.  The reference has no FFI: its "operator" is the
+ * Python call  Epipolar.forward(feat1, feat2, P1, P2, ...)  at
+ *   /root/reference/modeling/layers/epipolar.py:82          (the forward being replaced)
+ *   /root/reference/modeling/layers/epipolar.py:323-418     (grid2sample_locs — fused in-kernel)
+ *   /root/reference/modeling/layers/epipolar.py:272-321     (epipolar_similarity — fused)
+ *   /root/reference/modeling/layers/epipolar.py:248-255     (z conv + BN + residual — epilogue)
+ *   /root/reference/vision/multiview.py:16-21,25-57,154-163 (camera_center / normalize /
+ *                                                            de_normalize / pix2coord / coord2pix)
+ *   /root/reference/modeling/backbones/resnet.py:385-388    (caller residual `ret + feat`)
+ * A maintainer binds these symbols with ctypes; the host side shipped
+ * here (epipolar_transformers_b200/epipolar.py) does exactly that.
+ *
+ * Conventions: plain pointers + sizes, no torch types.  All tensor pointers are DEVICE
+ * pointers to float32 unless a name ends in _host.  The library never allocates persistent
+ * device memory; the caller passes a workspace.  Every entry point is re-entrant, takes the
+ * CUDA stream explicitly, never synchronises the device, and returns 0 on success or a
+ * negative EPI_E* code (epi_last_error() gives a thread-local message).
+ */
+#ifndef EPIPOLAR_B200_H_
+#define EPIPOLAR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EPI_ABI_VERSION 1
+
+#define EPI_OK 0
+#define EPI_EINVAL (-1)       /* bad argument / unsupported shape */
+#define EPI_EWORKSPACE (-2)   /* workspace too small */
+#define EPI_ECUDA (-3)        /* CUDA runtime error at launch (message has the cudaError string) */
+
+/* kernel variants (EpiFusionParams.variant) */
+#define EPI_VARIANT_AUTO 0
+#define EPI_VARIANT_WARP 1    /* one warp per reference pixel, online softmax (baseline kernel) */
+#define EPI_VARIANT_TILE 2    /* tiled kernel: shared-memory staged source taps, score interpolation */
+
+typedef struct EpiFusionParams {
+    /* ---- inputs ---------------------------------------------------------------------- */
+    const float *feat_ref;        /* [N,C,H,W] logical; element strides below (NCHW or channels-last) */
+    int64_t ref_stride[4];
+    const float *feat_src;        /* [N,C,H,W] logical */
+    int64_t src_stride[4];
+    const float *P_ref;           /* [N,3,4] contiguous: KRT of the reference view  (forward arg P1) */
+    const float *P_src;           /* [N,3,4] contiguous: KRT of the source view     (forward arg P2) */
+    const float *sample_locs_in;  /* optional [K,N,H,W,2] normalised grid coords: replaces the fused
+                                     geometry (parity protocol T1: inject the reference's own locations) */
+    /* ---- outputs --------------------------------------------------------------------- */
+    float *out;                   /* [N,C,H,W] logical, strides below */
+    int64_t out_stride[4];
+    float *attn;                  /* optional [N,K,H,W] contiguous: softmax weights ("depth", epipolar.py:263) */
+    float *corr_pos;              /* optional [N,H,W,2] contiguous: arg-max correspondence, feature px (:237-242) */
+    float *sample_locs_out;       /* optional [K,N,H,W,2] contiguous: locations actually sampled (:183) */
+    /* ---- optional folded eval-mode epilogue:  y = Wf·o + bf  (+ o if z_residual) ------ */
+    const float *z_weight_folded; /* [C,C] row-major (out_ch, in_ch) = diag(gamma/sqrt(var+eps))·Wz, or NULL */
+    const float *z_bias_folded;   /* [C] */
+    /* ---- scratch ---------------------------------------------------------------------- */
+    void *workspace;
+    size_t workspace_bytes;       /* >= epi_fusion_workspace_bytes(p) */
+    /* ---- shape & semantics ------------------------------------------------------------ */
+    int32_t N, C, H, W, K;
+    float downsample;             /* cfg.BACKBONE.DOWNSAMPLE */
+    float img_scale;              /* cfg.DATASETS.IMAGE_RESIZE * PREDICT_RESIZE */
+    float eps;                    /* 1e-3, epipolar.py:20 */
+    float softmax_scale;          /* cfg.EPIPOLAR.SOFTMAXSCALE (0.125) */
+    int32_t align_corners;        /* grid_sample semantics (torch>=1.3 default 0) */
+    int32_t correct_normalize;    /* cfg.EPIPOLAR.USE_CORRECT_NORMALIZE */
+    int32_t z_residual;           /* cfg.EPIPOLAR.ZRESIDUAL (only with z_weight_folded) */
+    int32_t add_ref_residual;     /* 1: also add feat_ref (the caller's `ret + feat`, resnet.py:388) */
+    int32_t variant;              /* EPI_VARIANT_* */
+    int32_t reserved[3];
+} EpiFusionParams;
+
+/* ABI version of the loaded library (== EPI_ABI_VERSION it was built with). */
+int epi_version(void);
+
+/* Thread-local description of the last error returned on this thread. */
+const char *epi_last_error(void);
+
+/* Bytes of scratch the forward needs for these shapes/strides/flags (0 is possible). */
+size_t epi_fusion_workspace_bytes(const EpiFusionParams *p);
+
+/* The fused forward: geometry + K bilinear taps + softmax(QK)·V (+ z/BN epilogue, + residuals).
+ * Replaces Epipolar.forward for ATTENTION='avg', SIMILARITY='dot', SOFTMAX_ENABLED.
+ * Asynchronous on `stream` (a cudaStream_t); returns launch-time errors only. */
+int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream);
+
+/* Only the geometry: sample locations [K,N,H,W,2] for (P_ref,P_src)  (grid2sample_locs). */
+int epi_sample_locs_f32(const float *P_ref, const float *P_src, float *sample_locs_out, int32_t N,
+                        int32_t H, int32_t W, int32_t K, float downsample, float img_scale, float eps,
+                        int32_t correct_normalize, void *stream);
+
+/* Fold conv1x1 z + eval BatchNorm into (Wf, bf) on the device, no host sync:
+ *   Wf[o,c] = s[o]·Wz[o,c],  bf[o] = s[o]·(bz[o] − mean[o]) + beta[o],  s = gamma/sqrt(var+bn_eps). */
+int epi_fold_z_bn_f32(const float *z_weight, const float *z_bias, const float *bn_weight,
+                      const float *bn_bias, const float *bn_mean, const float *bn_var, float bn_eps,
+                      int32_t C, float *w_folded, float *b_folded, void *stream);
+
+/* Number of kernels the last successful epi_fusion_forward_f32 on this thread launched. */
+int epi_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EPIPOLAR_B200_H_ */

@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library loads, exports every symbol include/epipolar_b200.h declares, its struct
+mirror matches, and argument validation works without touching a GPU."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from epipolar_transformers_b200 import _lib, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "epipolar_b200.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load()
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(epi_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported(lib):
+    names = declared_functions()
+    assert set(names) == set(_lib.EXPORTS)
+    for n in names:
+        assert hasattr(lib, n), n
+    assert lib.epi_version() == _lib.EPI_ABI_VERSION
+
+
+def test_struct_layout_matches_header():
+    """field order/types of the ctypes mirror follow the header's struct, and the size agrees with a C compile."""
+    import subprocess, tempfile
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "sz.c")
+        open(c, "w").write('#include <stdio.h>\n#include "%s"\nint main(){printf("%%zu %%zu %%zu", sizeof(EpiFusionParams),'
+                           ' __builtin_offsetof(EpiFusionParams, N), __builtin_offsetof(EpiFusionParams, variant));return 0;}' % HEADER)
+        exe = os.path.join(d, "sz")
+        subprocess.check_call(["gcc", c, "-o", exe])
+        size, off_n, off_var = map(int, subprocess.check_output([exe]).split())
+    assert ctypes.sizeof(_lib.EpiFusionParams) == size
+    assert _lib.EpiFusionParams.N.offset == off_n
+    assert _lib.EpiFusionParams.variant.offset == off_var
+
+
+def test_validation_without_gpu(lib):
+    p = _lib.EpiFusionParams()
+    assert lib.epi_fusion_forward_f32(ctypes.byref(p), None) == -1          # EPI_EINVAL: null tensors
+    assert b"non-null" in lib.epi_last_error()
+    buf = (ctypes.c_float * 4)()
+    addr = ctypes.addressof(buf)
+    p.feat_ref = addr; p.feat_src = addr; p.out = addr; p.P_ref = addr; p.P_src = addr
+    p.N, p.C, p.H, p.W, p.K = 1, 8, 8, 8, 1
+    p.downsample = 4.0; p.img_scale = 1.0
+    assert lib.epi_fusion_forward_f32(ctypes.byref(p), None) == -1          # K out of range
+    assert b"SAMPLESIZE" in lib.epi_last_error()
+    p.K = 8; p.C = 2000
+    assert lib.epi_fusion_forward_f32(ctypes.byref(p), None) == -1
+    assert lib.epi_fold_z_bn_f32(None, None, None, None, None, None, 1e-5, 8, None, None, None) == -1
+    assert lib.epi_sample_locs_f32(None, None, None, 1, 8, 8, 8, 4.0, 1.0, 1e-3, 0, None) == -1
+
+
+def test_workspace_plan(lib):
+    p = _lib.EpiFusionParams()
+    p.N, p.C, p.H, p.W, p.K = 4, 256, 64, 64, 64
+    buf = (ctypes.c_float * 4)()
+    p.feat_src = ctypes.addressof(buf)
+    p.src_stride = (ctypes.c_int64 * 4)(256 * 4096, 4096, 64, 1)           # NCHW: needs staging
+    m = 4 * 256 * 64 * 64 * 4
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == m
+    p.z_weight_folded = ctypes.addressof(buf)
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 2 * m
+    p.src_stride = (ctypes.c_int64 * 4)(256 * 4096, 1, 64 * 256, 256)      # channels_last: zero-copy
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == m
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(RuntimeError, match="no CPU/PyTorch fallback"):
+        _lib.load()

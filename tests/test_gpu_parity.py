@@ -1,0 +1,224 @@
+"""GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against
+(a) golden vectors frozen from the reference and (b) the CPU oracle on the same seeded inputs.
+
+Protocol (fp32, tolerance 1e-4 relative to max|ref| as north_star states):
+  T1  inject the reference's own sample locations -> out / attn / corr_pos vs reference
+  T2  fused geometry vs the reference's geometry evaluated in fp64 (feature-pixel error)
+  T3  end to end: kernel's own locations are emitted, the oracle consumes them, strict compare
+"""
+import numpy as np
+import pytest
+import torch
+
+import epipolar_transformers_b200 as epi
+from oracle import c_oracle, epipolar_oracle as eo, golden_cases as gc
+from tests.util import load_golden, px_err, rel_max
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-4
+FULL = [n for n, s in gc.CASES.items() if s["full"]]
+BIG = [n for n, s in gc.CASES.items() if not s["full"]]
+VARIANTS = ["warp", "auto"]
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def fold_params(params, zres, bn_eps=1e-5):
+    s = params["bn.weight"] / np.sqrt(params["bn.running_var"] + bn_eps)
+    wf = (s[:, None] * params["z.weight"].reshape(len(s), -1)).astype(np.float32)
+    bf = (s * (params["z.bias"] - params["bn.running_mean"]) + params["bn.bias"]).astype(np.float32)
+    return dev(wf), dev(bf)
+
+
+def run_kernel(name, locs_in=None, variant="auto", want_locs=True, channels_last=False, **kw):
+    cfg, f1, f2, P1, P2, params = gc.build_inputs(name)
+    spec = gc.CASES[name]
+    t1, t2 = dev(f1), dev(f2)
+    if channels_last:
+        t1 = t1.contiguous(memory_format=torch.channels_last)
+        t2 = t2.contiguous(memory_format=torch.channels_last)
+    zf = fold_params(params, spec["zres"]) if params else None
+    out, corr, attn, locs = epi.epipolar_fusion(
+        t1, t2, dev(P1), dev(P2), K=spec["K"], downsample=cfg.BACKBONE.DOWNSAMPLE,
+        img_scale=cfg.DATASETS.IMAGE_RESIZE * cfg.DATASETS.PREDICT_RESIZE, softmax_scale=cfg.EPIPOLAR.SOFTMAXSCALE,
+        correct_normalize=spec["correct"], z_folded=zf, z_residual=spec["zres"],
+        sample_locs_in=dev(locs_in) if locs_in is not None else None, want_locs=want_locs, variant=variant, **kw)
+    torch.cuda.synchronize()
+    return (cfg, f1, f2, P1, P2, params), dict(out=out.cpu().numpy(), corr_pos=corr.cpu().numpy(), attn=attn.cpu().numpy(),
+                                               sample_locs=locs.cpu().numpy() if locs is not None else None)
+
+
+def corr_agree(got, want):
+    """fraction of pixels whose arg-max correspondence is identical (ties between equal softmax
+    weights may legitimately resolve to another sample)."""
+    return float((np.abs(got - want).max(-1) < 1e-3).mean())
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("name", FULL)
+def test_T1_golden_full(name, variant):
+    g = load_golden(name)
+    _, r = run_kernel(name, locs_in=g["sample_locs"], variant=variant)
+    assert rel_max(r["out"], g["out"]) < TOL
+    assert rel_max(r["attn"], g["attn"]) < TOL
+    assert corr_agree(r["corr_pos"], g["corr_pos"]) > 0.99
+    np.testing.assert_array_equal(r["sample_locs"], g["sample_locs"])     # pass-through of injected locations
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("name", BIG)
+def test_T1_golden_subsampled(name, variant):
+    """BASELINE-sized shapes: the reference's frozen locations are injected at the frozen pixels
+    (the kernel's own geometry everywhere else) and compared there."""
+    g = load_golden(name)
+    spec = gc.CASES[name]
+    _, own = run_kernel(name, variant=variant)
+    locs = own["sample_locs"].copy()
+    px = g["pixels"]; n_idx = np.arange(spec["N"])[:, None]
+    locs.transpose(1, 2, 3, 0, 4)[n_idx, px[..., 0], px[..., 1]] = g["sample_locs"]
+    _, r = run_kernel(name, locs_in=locs, variant=variant)
+    assert rel_max(r["out"][n_idx, :, px[..., 0], px[..., 1]], g["out"]) < TOL
+    assert rel_max(r["attn"][n_idx, :, px[..., 0], px[..., 1]], g["attn"]) < TOL
+    assert corr_agree(r["corr_pos"][n_idx, px[..., 0], px[..., 1]], g["corr_pos"]) > 0.97
+
+
+@pytest.mark.parametrize("name", FULL + BIG)
+def test_T2_geometry_vs_fp64(name):
+    """Fused fp32 geometry must be at least as close to the fp64 truth as the reference's own
+    fp32 locations are (and < 1e-3 feature px on camera-like KRTs)."""
+    g = load_golden(name)
+    spec = gc.CASES[name]
+    H, W = spec["H"], spec["W"]
+    cfg, _, _, P1, P2, _ = gc.build_inputs(name)
+    locs = epi.sample_locs(dev(P1), dev(P2), H, W, spec["K"], cfg.BACKBONE.DOWNSAMPLE,
+                           cfg.DATASETS.IMAGE_RESIZE * cfg.DATASETS.PREDICT_RESIZE, spec["correct"]).cpu().numpy()
+    _, r = run_kernel(name, variant="warp")
+    np.testing.assert_array_equal(locs, r["sample_locs"])                 # both entry points share the device code
+    if not spec["full"]:
+        px = g["pixels"]; n_idx = np.arange(spec["N"])[:, None]
+        locs = locs.transpose(1, 2, 3, 0, 4)[n_idx, px[..., 0], px[..., 1]]
+    err, far_ok = px_err(locs, g["sample_locs_fp64"], H, W)
+    ref_err, _ = px_err(g["sample_locs"], g["sample_locs_fp64"], H, W)
+    assert far_ok
+    if spec["cams"] == "randn":
+        assert err < 5e-3, (err, ref_err)
+    else:
+        assert err < 1e-3 and err <= max(ref_err, 1e-4), (err, ref_err)
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("name", FULL + BIG)
+def test_T3_end_to_end_vs_oracle(name, variant):
+    """Own geometry end to end: the locations the kernel sampled are fed to the C oracle."""
+    (cfg, f1, f2, P1, P2, params), r = run_kernel(name, variant=variant)
+    o = c_oracle.forward(cfg, f1, f2, P1, P2, locs=r["sample_locs"])
+    out = eo.z_epilogue(o["out"], params, cfg.EPIPOLAR.ZRESIDUAL) if params else o["out"]
+    assert rel_max(r["out"], out) < TOL
+    assert rel_max(r["attn"], o["attn"]) < TOL
+    assert corr_agree(r["corr_pos"], o["corr_pos"]) > 0.99
+    s = r["attn"].sum(1)
+    assert np.abs(s - 1).max() < 1e-5
+
+
+@pytest.mark.parametrize("name", ["tiny_ring_z", "tiny_randn_krt", "cfg1_ring"])
+def test_channels_last_and_residual(name):
+    """channels_last strides (zero-copy source) and the fused caller residual give the same numbers."""
+    _, base = run_kernel(name)
+    (_, f1, _, _, _, _), cl = run_kernel(name, channels_last=True)
+    assert rel_max(cl["out"], base["out"]) < 1e-6
+    assert rel_max(cl["attn"], base["attn"]) < 1e-6
+    _, res = run_kernel(name, add_ref_residual=True)
+    assert rel_max(res["out"], base["out"] + f1) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["tiny_ring_z", "tiny_ds8_resize"])
+def test_align_corners_true(name):
+    """torch<=1.2 grid_sample semantics as a kernel parameter, vs the numpy oracle."""
+    (cfg, f1, f2, P1, P2, params), r = run_kernel(name, align_corners=True)
+    o = eo.forward(cfg, f1, f2, P1, P2, params=params, locs=r["sample_locs"], align_corners=True)
+    assert rel_max(r["out"], o["out"]) < TOL
+    assert rel_max(r["attn"], o["attn"]) < TOL
+
+
+def test_module_contract_and_state_dict():
+    """nn.Module drop-in: reference parameter names load, 4-tuple contract, eval fold == oracle."""
+    name = "tiny_ring_z"
+    cfg, f1, f2, P1, P2, params = gc.build_inputs(name)
+    cfg.VIS.EPIPOLAR_LINE = True
+    m = epi.Epipolar(cfg=cfg).cuda().eval()
+    sd = {k: torch.from_numpy(v) for k, v in params.items()}
+    missing = m.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and set(missing.missing_keys) <= {"bn.num_batches_tracked"}
+    with torch.no_grad():
+        out, corr, attn, locs_t = m(dev(f1), dev(f2), dev(P1), dev(P2), camera=None, other_camera=None)
+    N, C, H, W = f1.shape
+    K = cfg.EPIPOLAR.SAMPLESIZE
+    assert out.shape == (N, C, H, W) and corr.shape == (N, H, W, 2) and attn.shape == (N, K, H, W)
+    assert locs_t.shape == (N, K, H, W, 2)
+    locs = locs_t.transpose(0, 1).contiguous().cpu().numpy()
+    o = eo.forward(cfg, f1, f2, P1, P2, params=params, locs=locs)
+    assert rel_max(out.cpu().numpy(), o["out"]) < TOL
+    # default zero-init BN: z branch contributes nothing, finalout == out (epipolar.py:249-253, BN.py:48-52)
+    m0 = epi.Epipolar(cfg=cfg).cuda().eval()
+    with torch.no_grad():
+        out0 = m0(dev(f1), dev(f2), dev(P1), dev(P2))[0]
+    o0 = c_oracle.forward(cfg, f1, f2, P1, P2, locs=locs)
+    assert rel_max(out0.cpu().numpy(), o0["out"]) < TOL
+    # train mode keeps conv/BN in PyTorch (batch statistics)
+    m.train()
+    with torch.no_grad():
+        out_tr = m(dev(f1), dev(f2), dev(P1), dev(P2))[0]
+    pre = torch.from_numpy(o0["out"]).cuda()
+    ref_tr = torch.nn.functional.batch_norm(torch.nn.functional.conv2d(pre, m.z.weight, m.z.bias), None, None,
+                                            m.bn.weight, m.bn.bias, True, 0.1, 1e-5) + pre
+    assert rel_max(out_tr.cpu().numpy(), ref_tr.cpu().numpy()) < 1e-3
+
+
+def test_errors_are_loud():
+    cfg = epi.make_cfg(EPIPOLAR=dict(ATTENTION="max"))
+    with pytest.raises(NotImplementedError):
+        epi.Epipolar(cfg=cfg)
+    m = epi.Epipolar(cfg=epi.make_cfg(KEYPOINT=dict(HEATMAP_SIZE=(8, 8), NFEATS=8), EPIPOLAR=dict(SAMPLESIZE=8)))
+    x = torch.zeros(1, 8, 8, 8)
+    with pytest.raises(RuntimeError):
+        m(x, x, torch.zeros(1, 3, 4), torch.zeros(1, 3, 4))             # CPU tensors: no CPU path
+    with pytest.raises(RuntimeError):
+        epi.epipolar_fusion(x.cuda(), x.cuda(), torch.zeros(1, 3, 4), torch.zeros(1, 3, 4), K=1)   # EPI_EINVAL
+
+
+# ---- size-independent properties at BASELINE.json's full shapes --------------------------------
+@pytest.mark.parametrize("shape", [(4, 256, 64, 64, 64), (4, 256, 96, 96, 64)])
+def test_full_size_properties(shape):
+    N, C, H, W, K = shape
+    from epipolar_transformers_b200 import synthetic as syn
+    P1, P2 = syn.pairs_from_ring(N, 4 * H)
+    f1 = dev(syn.features(N, C, H, W, "randn", 3)); f2 = dev(syn.features(N, C, H, W, "randn", 4))
+    kw = dict(K=K, correct_normalize=True, want_locs=True)
+    out, corr, attn, locs = epi.epipolar_fusion(f1, f2, dev(P1), dev(P2), **kw)
+    # (a) softmax weights sum to one, correspondences lie in the map
+    assert (attn.sum(1) - 1).abs().max().item() < 1e-5
+    assert corr.min().item() > -1.0 and corr[..., 0].max().item() < W and corr[..., 1].max().item() < H
+    # (b) run-to-run determinism, bit exact
+    out2 = epi.epipolar_fusion(f1, f2, dev(P1), dev(P2), **kw)[0]
+    assert torch.equal(out, out2)
+    # (c) pairs are independent: permuting the batch permutes the outputs, bit exact
+    perm = torch.tensor([2, 0, 3, 1], device="cuda")
+    outp = epi.epipolar_fusion(f1[perm].contiguous(), f2[perm].contiguous(), dev(P1)[perm], dev(P2)[perm], **kw)[0]
+    assert torch.equal(outp, out[perm])
+    # (d) a spatially constant source map is reproduced wherever all K samples are in bounds
+    v = torch.randn(1, C, 1, 1, device="cuda")
+    #     (USE_CORRECT_NORMALIZE=False + align_corners=False maps border pixel centres onto border taps exactly)
+    kwd = dict(kw, correct_normalize=False)
+    outc, _, _, locs = epi.epipolar_fusion(f1, v.expand(N, C, H, W).contiguous(), dev(P1), dev(P2), **kwd)
+    lim = torch.tensor([1 - 1.0 / W, 1 - 1.0 / H], device="cuda") + 1e-5
+    inb = (locs.abs() <= lim).all(-1).all(0)                            # [N,H,W]: every sample inside the map
+    assert inb.float().mean().item() > 0.2
+    err = (outc - v).abs().amax(1)[inb].max().item()
+    assert err < 1e-4 * v.abs().max().item()
+    # (e) linear in the source "values" when the logits are unchanged: zero query => uniform attention
+    outz, _, attnz, _ = epi.epipolar_fusion(torch.zeros_like(f1), f2, dev(P1), dev(P2), **kw)
+    assert (attnz - 1.0 / K).abs().max().item() < 1e-7
+    outz2 = epi.epipolar_fusion(torch.zeros_like(f1), 2 * f2, dev(P1), dev(P2), **kw)[0]
+    assert (outz2 - 2 * outz).abs().max().item() < 1e-5

@@ -86,3 +86,27 @@ def test_c_oracle_T1_subsampled(name):
     got_attn = o["attn"][n_idx, :, px[..., 0], px[..., 1]]
     assert rel_max(got_out, g["out"]) < 1e-5
     assert rel_max(got_attn, g["attn"]) < 1e-5
+
+
+@pytest.mark.parametrize("name", FULL)
+def test_torch_port_T1_full(name):
+    """the CPU-baseline port (same ATen op sequence as the reference) reproduces the golden vectors."""
+    import torch
+    from oracle import torch_port
+    g = load_golden(name)
+    cfg, f1, f2, P1, P2, params = gc.build_inputs(name)
+    out, corr, attn = torch_port.forward(cfg, torch.from_numpy(f1), torch.from_numpy(f2), P1, P2, params=params,
+                                         locs=g["sample_locs"])
+    assert rel_max(out.numpy(), g["out"]) < 2e-6
+    assert rel_max(attn.numpy(), g["attn"]) < 2e-6
+    assert (np.abs(corr.numpy() - g["corr_pos"]).max(-1) < 1e-4).mean() > 0.995
+
+
+def test_torch_port_own_geometry_close_to_reference():
+    import torch
+    from oracle import torch_port
+    name = "tiny_ring_z"
+    g = load_golden(name)
+    cfg, f1, f2, P1, P2, params = gc.build_inputs(name)
+    out, _, attn = torch_port.forward(cfg, torch.from_numpy(f1), torch.from_numpy(f2), P1, P2, params=params)
+    assert rel_max(attn.numpy(), g["attn"]) < 5e-2       # fp32 pinv geometry noise (SURVEY fact 10), not a parity bar
