@@ -16,7 +16,7 @@ EPI_VARIANT_AUTO, EPI_VARIANT_WARP, EPI_VARIANT_TILE = 0, 1, 2
 VARIANTS = {"auto": EPI_VARIANT_AUTO, "warp": EPI_VARIANT_WARP, "tile": EPI_VARIANT_TILE}
 
 EXPORTS = ("epi_version", "epi_last_error", "epi_fusion_workspace_bytes", "epi_fusion_forward_f32",
-           "epi_sample_locs_f32", "epi_fold_z_bn_f32", "epi_last_launch_count")
+           "epi_sample_locs_f32", "epi_fold_z_bn_f32", "epi_last_launch_count", "epi_umma_selftest")
 
 _fp = ctypes.POINTER(ctypes.c_float)
 
@@ -68,6 +68,9 @@ def load():
     lib.epi_fold_z_bn_f32.restype = ctypes.c_int
     lib.epi_fold_z_bn_f32.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_float, ctypes.c_int32, ctypes.c_void_p,
                                                              ctypes.c_void_p, ctypes.c_void_p]
+    lib.epi_umma_selftest.restype = ctypes.c_int
+    lib.epi_umma_selftest.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_void_p]
     v = lib.epi_version()
     if v != EPI_ABI_VERSION:
         raise RuntimeError("libepipolar_b200.so ABI version %d != expected %d" % (v, EPI_ABI_VERSION))

@@ -101,6 +101,11 @@ int epi_fold_z_bn_f32(const float *z_weight, const float *z_bias, const float *b
                       const float *bn_bias, const float *bn_mean, const float *bn_var, float bn_eps,
                       int32_t C, float *w_folded, float *b_folded, void *stream);
 
+/* Diagnostic: one-CTA tcgen05 GEMM in the exact operand forms the fusion kernel uses
+ * (mode 0: D[128,N] = A[128,K]·B[N,K]^T, both K-major;  mode 1: D[128,N] = At[K,128]^T·B[N,K]^T, A MN-major;
+ * split=1: bf16 (hi,lo) three-term products).  All pointers device fp32, row-major. */
+int epi_umma_selftest(int mode, const float *A, const float *B, float *D, int N, int K, int split, void *stream);
+
 /* Number of kernels the last successful epi_fusion_forward_f32 on this thread launched. */
 int epi_last_launch_count(void);
 

