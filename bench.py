@@ -219,12 +219,13 @@ def run_ours(args, wl):
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     refs = [torch.relu(torch.randn(N, C, H, W, device=dev, generator=gen)) for _ in range(n_sets)]
     srcs = [torch.relu(torch.randn(N, C, H, W, device=dev, generator=gen)) for _ in range(n_sets)]
-    gathered = torch.empty((world, N, C, H, W), device=dev) if world > 1 else None
+    gathered_flat = torch.empty((world * N, C, H, W), device=dev) if world > 1 else None
+    gathered = gathered_flat.view(world, N, C, H, W) if world > 1 else None
 
     def step(i):
         f_ref = refs[i % n_sets]
         if world > 1:
-            dist.all_gather_into_tensor(gathered, f_ref)           # exchange per-view feature maps (NVLink)
+            dist.all_gather_into_tensor(gathered_flat, f_ref)           # exchange per-view feature maps (NVLink)
             f_src = gathered[src_of[rank]]
         else:
             f_src = srcs[i % n_sets]
@@ -284,7 +285,7 @@ def run_ours(args, wl):
     def e2e_step(i):
         d_ref = h_ref[i % 2].to(dev, non_blocking=True)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, d_ref)
+            dist.all_gather_into_tensor(gathered_flat, d_ref)
             d_src = gathered[src_of[rank]]
         else:
             d_src = h_src[i % 2].to(dev, non_blocking=True)

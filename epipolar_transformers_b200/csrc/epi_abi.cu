@@ -27,13 +27,19 @@ bool src_is_channels_last(const EpiFusionParams *p) {
 
 struct Plan {
     size_t off_src = 0, off_prez = 0, total = 0;
-    bool stage_src = false, has_z = false;
+    bool stage_src = false, has_z = false, tile = false;
 };
+
+bool want_tile(const EpiFusionParams *p) {
+    if (p->variant == EPI_VARIANT_WARP) return false;
+    return epi::fusion_tile_shape_ok(p->C, p->H, p->W, p->K, p->sample_locs_in != nullptr);
+}
 
 Plan make_plan(const EpiFusionParams *p) {
     Plan pl;
     const size_t map = (size_t)p->N * p->C * p->H * p->W * sizeof(float);
-    pl.stage_src = !src_is_channels_last(p);
+    pl.tile = want_tile(p);
+    pl.stage_src = pl.tile || !src_is_channels_last(p);      // tile kernel: bf16 (hi, lo) planes, same bytes as one fp32 map
     pl.has_z = p->z_weight_folded != nullptr;
     size_t off = 0;
     if (pl.stage_src) { pl.off_src = off; off += align_up(map); }
@@ -61,6 +67,11 @@ epi::GeomCfg make_geom(int H, int W, int K, float ds, float r, float eps, int co
     g.xmin = epi::pix2coord(0, ds, r); g.xmax = epi::pix2coord(W - 1, ds, r);
     g.ymin = epi::pix2coord(0, ds, r); g.ymax = epi::pix2coord(H - 1, ds, r);
     g.correct = correct; g.align = align; g.H = H; g.W = W; g.K = K;
+    // pix = (v/r + 0.5 - ds/2)/ds ;  g = -1 + 2 pix/(size-1)  |  -1 + 2 (pix+0.5)/size      (multiview.py:25-37,159-163)
+    g.inv_rds = (float)(1.0 / ((double)r * ds));
+    g.off_ds = (float)((0.5 - (double)ds / 2.0) / ds);
+    if (correct) { g.gsx = (float)(2.0 / (W - 1)); g.gox = -1.f; g.gsy = (float)(2.0 / (H - 1)); g.goy = -1.f; }
+    else { g.gsx = (float)(2.0 / W); g.gox = (float)(-1.0 + 1.0 / W); g.gsy = (float)(2.0 / H); g.goy = (float)(-1.0 + 1.0 / H); }
     return g;
 }
 
@@ -99,7 +110,15 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
     for (int i = 0; i < 4; i++) a.ref_stride[i] = p->ref_stride[i];
     a.geom = make_geom(p->H, p->W, p->K, p->downsample, p->img_scale, p->eps, p->correct_normalize, p->align_corners);
 
-    if (pl.stage_src) {
+    if (p->variant == EPI_VARIANT_TILE && !pl.tile) return fail(EPI_EINVAL, "tile variant does not support this shape");
+    if (pl.tile) {
+        __nv_bfloat16 *hi = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_src);
+        __nv_bfloat16 *lo = hi + (size_t)p->N * p->C * p->H * p->W;
+        e = epi::launch_split_planes(p->feat_src, p->src_stride, hi, lo, p->N, p->C, p->H, p->W, st);
+        if (e != cudaSuccess) return fail(EPI_ECUDA, "operand staging launch failed: %s", cudaGetErrorString(e));
+        launches++;
+        a.src_hi = hi; a.src_lo = lo;
+    } else if (pl.stage_src) {
         float *nhwc = reinterpret_cast<float *>(ws + pl.off_src);
         e = epi::launch_nchw_to_nhwc(p->feat_src, p->src_stride, nhwc, p->N, p->C, p->H, p->W, st);
         if (e != cudaSuccess) return fail(EPI_ECUDA, "layout staging launch failed: %s", cudaGetErrorString(e));
@@ -109,7 +128,13 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
         a.src_nhwc = p->feat_src;
     }
 
-    if (pl.has_z) {     // fused feature goes to the pre-z buffer (contiguous NCHW), epilogue writes `out`
+    const bool z_tc = pl.has_z && pl.tile && epi::zgemm_supported(p->C);
+    if (z_tc) {         // fused feature leaves the tile kernel as bf16 (hi, lo) planes: the A operand of the z GEMM
+        a.out = nullptr;
+        a.out_hi = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_prez);
+        a.out_lo = a.out_hi + (size_t)p->N * p->C * p->H * p->W;
+        a.add_ref = 0;
+    } else if (pl.has_z) {     // fused feature goes to the pre-z buffer (contiguous NCHW), epilogue writes `out`
         a.out = reinterpret_cast<float *>(ws + pl.off_prez);
         a.out_stride[0] = (int64_t)p->C * p->H * p->W; a.out_stride[1] = (int64_t)p->H * p->W;
         a.out_stride[2] = p->W; a.out_stride[3] = 1;
@@ -120,18 +145,24 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
         a.add_ref = p->add_ref_residual;
     }
 
-    bool use_tile = false;
-    if (p->variant == EPI_VARIANT_TILE) {
-        if (!epi::fusion_tile_supported(a)) return fail(EPI_EINVAL, "tile variant does not support this shape");
-        use_tile = true;
-    } else if (p->variant == EPI_VARIANT_AUTO) {
-        use_tile = epi::fusion_tile_supported(a);
-    }
+    const bool use_tile = pl.tile && epi::fusion_tile_supported(a);
+    if (pl.tile && !use_tile) return fail(EPI_EINVAL, "internal: tile plan without tile support");
     e = use_tile ? epi::launch_fusion_tile(a, st) : epi::launch_fusion_warp(a, st);
     if (e != cudaSuccess) return fail(EPI_ECUDA, "fusion kernel launch failed: %s", cudaGetErrorString(e));
     launches++;
 
-    if (pl.has_z) {
+    if (z_tc) {
+        epi::ZGemmArgs z;
+        memset(&z, 0, sizeof(z));
+        z.x_hi = a.out_hi; z.x_lo = a.out_lo; z.Wf = p->z_weight_folded; z.bf = p->z_bias_folded;
+        z.ref = p->feat_ref; z.y = p->out;
+        for (int i = 0; i < 4; i++) { z.y_stride[i] = p->out_stride[i]; z.ref_stride[i] = p->ref_stride[i]; }
+        z.N = p->N; z.C = p->C; z.HW = p->H * p->W; z.W = p->W; z.Npad = p->C;
+        z.z_residual = p->z_residual; z.add_ref = p->add_ref_residual;
+        e = epi::launch_zgemm(z, st);
+        if (e != cudaSuccess) return fail(EPI_ECUDA, "z GEMM launch failed: %s", cudaGetErrorString(e));
+        launches++;
+    } else if (pl.has_z) {
         epi::ZArgs z;
         memset(&z, 0, sizeof(z));
         z.x = a.out;

@@ -37,6 +37,52 @@ cudaError_t launch_nchw_to_nhwc(const float *src, const int64_t stride[4], float
 }
 
 // ------------------------------------------------------------------------------------------
+// [N,C,H,W] fp32 (any strides) -> two bf16 planes [N,H,W,C] with src ≈ hi + lo (operands of the
+// tensor-core kernel; |src - hi - lo| <~ 2^-17 |src|).  Same 32x32 transpose tile as above.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_planes_kernel(const float *__restrict__ src, int64_t sn, int64_t sc, int64_t sh,
+                                                           int64_t sw, __nv_bfloat16 *__restrict__ hi,
+                                                           __nv_bfloat16 *__restrict__ lo, int C, int H, int W) {
+    __shared__ float tile[32][33];
+    const int HW = H * W;
+    const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const float *s = src + (int64_t)n * sn;
+    if (sc != 1) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int c = c0 + ty + i * 8, p = p0 + tx;
+            tile[ty + i * 8][tx] = (c < C && p < HW) ? __ldg(s + c * sc + (p / W) * sh + (p % W) * sw) : 0.f;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            int p = p0 + ty + i * 8, c = c0 + tx;
+            tile[tx][ty + i * 8] = (c < C && p < HW) ? __ldg(s + c + (p / W) * sh + (p % W) * sw) : 0.f;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int p = p0 + ty + i * 8, c = c0 + tx;
+        if (c < C && p < HW) {
+            const float v = tile[tx][ty + i * 8];
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const size_t o = ((size_t)n * HW + p) * C + c;
+            hi[o] = h;
+            lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+        }
+    }
+}
+
+cudaError_t launch_split_planes(const float *src, const int64_t stride[4], __nv_bfloat16 *hi, __nv_bfloat16 *lo, int N, int C,
+                                int H, int W, cudaStream_t st) {
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32, N);
+    split_planes_kernel<<<grid, 256, 0, st>>>(src, stride[0], stride[1], stride[2], stride[3], hi, lo, C, H, W);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // Fold conv1x1 z + eval BN (epipolar.py:250-251, BN.py:79 with training=False) into Wf, bf.
 // ------------------------------------------------------------------------------------------
 __global__ void fold_z_bn_kernel(const float *__restrict__ zw, const float *__restrict__ zb,
@@ -137,7 +183,7 @@ __global__ void __launch_bounds__(256) sample_locs_kernel(const float *__restric
     for (int k = 0; k < gc.K; k++) {
         float t = (float)k / (float)(gc.K - 1);
         reinterpret_cast<float2 *>(locs)[((size_t)k * N + n) * HW + p] =
-            make_float2(img2grid(sx + (ex - sx) * t, gc, gc.W), img2grid(sy + (ey - sy) * t, gc, gc.H));
+            make_float2(img2grid_x(sx + (ex - sx) * t, gc), img2grid_y(sy + (ey - sy) * t, gc));
     }
 }
 

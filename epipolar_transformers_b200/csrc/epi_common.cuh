@@ -22,6 +22,8 @@ struct PairGeom {
 // Launch-invariant geometry configuration.
 struct GeomCfg {
     float ds, r, eps;
+    float inv_rds, off_ds;          // image coord -> feature px:  pix = v*inv_rds + off_ds
+    float gsx, gox, gsy, goy;       // feature px -> grid coord:   g = pix*gs + go   (per axis)
     float xmin, xmax, ymin, ymax;   // image coords of first/last pixel centres (epipolar.py:46-49)
     int correct;                    // USE_CORRECT_NORMALIZE
     int align;                      // grid_sample align_corners
@@ -91,10 +93,10 @@ __device__ __forceinline__ void line_endpoints(const PairGeom &g, const GeomCfg 
 }
 
 // image coordinate of sample k -> normalised grid_sample coordinate (:405-415, multiview.py:25-37,159-163)
-__device__ __forceinline__ float img2grid(float v, const GeomCfg &c, int size) {
-    float pix = (v / c.r + 0.5f - c.ds * 0.5f) / c.ds;
-    return c.correct ? (-1.f + 2.f * pix / (float)(size - 1)) : (-1.f + 2.f * (pix + 0.5f) / (float)size);
-}
+// Evaluated with host-precomputed reciprocals (a couple of ulp from the reference's division chain,
+// i.e. ~1e-6 feature px; the emitted sample_locs are exactly what the kernels sample).
+__device__ __forceinline__ float img2grid_x(float v, const GeomCfg &c) { return fmaf(fmaf(v, c.inv_rds, c.off_ds), c.gsx, c.gox); }
+__device__ __forceinline__ float img2grid_y(float v, const GeomCfg &c) { return fmaf(fmaf(v, c.inv_rds, c.off_ds), c.gsy, c.goy); }
 
 // normalised grid coordinate -> source feature-pixel coordinate (ATen grid_sampler unnormalize)
 __device__ __forceinline__ float grid2pix(float g, int size, int align) {

@@ -115,8 +115,8 @@ epi_fusion_warp_kernel(const FusionArgs a) {
                         gx = l.x; gy = l.y;
                     } else {
                         float t = (float)k / (float)(K - 1);
-                        gx = img2grid(sx + (ex - sx) * t, gc, W);
-                        gy = img2grid(sy + (ey - sy) * t, gc, H);
+                        gx = img2grid_x(sx + (ex - sx) * t, gc);
+                        gy = img2grid_y(sy + (ey - sy) * t, gc);
                     }
                     if (a.locs_out) reinterpret_cast<float2 *>(a.locs_out)[((size_t)k * a.N + n) * HW + p] = make_float2(gx, gy);
                 }

@@ -1,5 +1,7 @@
 // epi_kernels.cuh — internal launch interface between the C ABI (epi_abi.cu) and the kernels.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "epi_common.cuh"
 
 namespace epi {
@@ -7,10 +9,12 @@ namespace epi {
 // Device-side view of one fused forward (built from EpiFusionParams by the ABI layer).
 struct FusionArgs {
     const float *feat_ref;  int64_t ref_stride[4];
-    const float *src_nhwc;                    // [N,H,W,C] contiguous, 16-byte aligned (zero-copy or staged)
+    const float *src_nhwc;                    // [N,H,W,C] contiguous, 16-byte aligned (zero-copy or staged) — warp kernel
+    const __nv_bfloat16 *src_hi, *src_lo;     // [N,H,W,C] bf16 planes, src ≈ hi + lo — tile kernel
     const float *P_ref, *P_src;
     const float *locs_in;
     float *out;             int64_t out_stride[4];
+    __nv_bfloat16 *out_hi, *out_lo;           // optional: fused feature as bf16 (hi, lo) planes [N,H,W,C] (feeds the z GEMM)
     float *attn, *corr_pos, *locs_out;
     int N, C;
     float softmax_scale;
@@ -28,9 +32,24 @@ struct ZArgs {
     int z_residual, add_ref;
 };
 
+// tensor-core z-projection: x arrives as bf16 (hi, lo) planes [N,H,W,C] written by the tile kernel
+struct ZGemmArgs {
+    const __nv_bfloat16 *x_hi, *x_lo;
+    const float *Wf, *bf;
+    const float *ref;       int64_t ref_stride[4];
+    float *y;               int64_t y_stride[4];
+    int N, C, HW, W, Npad;
+    int z_residual, add_ref;
+};
+bool zgemm_supported(int C);
+cudaError_t launch_zgemm(const ZGemmArgs &z, cudaStream_t st);
+
 cudaError_t launch_fusion_warp(const FusionArgs &a, cudaStream_t st);
 cudaError_t launch_fusion_tile(const FusionArgs &a, cudaStream_t st);
 bool fusion_tile_supported(const FusionArgs &a);
+bool fusion_tile_shape_ok(int C, int H, int W, int K, bool has_locs_in);
+cudaError_t launch_split_planes(const float *src, const int64_t stride[4], __nv_bfloat16 *hi, __nv_bfloat16 *lo, int N, int C,
+                                int H, int W, cudaStream_t st);
 
 cudaError_t launch_nchw_to_nhwc(const float *src, const int64_t stride[4], float *dst, int N, int C, int H, int W, cudaStream_t st);
 cudaError_t launch_z_epilogue(const ZArgs &z, cudaStream_t st);

@@ -87,3 +87,50 @@ extern "C" int epi_umma_selftest(int mode, const float *A, const float *B, float
     epi::umma_selftest_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(mode, A, B, D, N, K, split);
     return cudaGetLastError() == cudaSuccess ? EPI_OK : EPI_ECUDA;
 }
+
+// ---- micro-benchmark: cycles per tcgen05.mma for M=128, K=16 bf16, N in {32..256}, A K-major or MN-major ----
+namespace epi {
+using namespace umma;
+__global__ void __launch_bounds__(128) umma_bench_kernel(int N, int reps, int mn_major, long long *out) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < (65536 + 32768) / 4; i += 128) reinterpret_cast<uint32_t *>(smem)[i] = 0x3f803f80u;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+    if (tid == 0) { mbar_init(&bar, 1); mbar_fence_init(); }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, N, mn_major, 0);
+        const uint32_t sa = smem_u32(smem), sb = sa + 65536;
+        long long t0 = clock64();
+        for (int r = 0; r < reps; r++) {
+            const int ks = r & 7;
+            const uint64_t ad = mn_major ? make_smem_desc(sa + ks * 2048, 16384, 1024) : make_smem_desc(sa + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024);
+            const uint64_t bd = make_smem_desc(sb + (ks & 3) * 32, 16, 1024);
+            mma_bf16(tmem, ad, bd, idesc, 1u);
+        }
+        long long t1 = clock64();
+        mma_commit(&bar);
+        out[1] = t1 - t0;
+        out[2] = t0;
+    }
+    mbar_wait(&bar, 0);
+    if (tid == 0) out[0] = clock64() - out[2];
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+}  // namespace epi
+
+extern "C" int epi_umma_bench(int N, int reps, int mn_major, long long *out_dev, void *stream) {
+    const size_t smem = 65536 + 32768 + 1024;
+    cudaFuncSetAttribute(epi::umma_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    epi::umma_bench_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(N, reps, mn_major, out_dev);
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}

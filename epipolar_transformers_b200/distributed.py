@@ -1,0 +1,69 @@
+"""One camera view per GPU: the only exchange step of the path.
+
+The reference shards the batch with single-process nn.DataParallel (/root/reference/modeling/model.py:44) and
+has no process groups.  Here every rank owns one view (its backbone output `feat_view [B,C,H,W]` for B frames and
+its `KRT [3,4]`), the ranks all-gather the feature maps over NCCL/NVLink, and each rank fuses its view against
+the map of its source view — the nearest camera centre, /root/reference/vision/multiview.py:59-83 and
+data/datasets/multiview_h36m.py:231-238 (TOPK=1) — with the single-GPU fused kernel.  No other collective exists
+on this path: pairs and pixels are independent.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .multiview import neighbor_cameras
+
+
+def source_view_table(KRT_all) -> np.ndarray:
+    """src(v) for every view: nearest other camera centre.  KRT_all: [V,3,4] (numpy or tensor, any device)."""
+    K = KRT_all.detach().cpu().numpy() if isinstance(KRT_all, torch.Tensor) else np.asarray(KRT_all)
+    K = K.astype(np.float64)
+    centers = np.stack([-np.linalg.solve(P[:, :3], P[:, 3]) for P in K])
+    return neighbor_cameras(centers, topk=1)[:, 0]
+
+
+class ViewParallelFusion:
+    """Holds the gather buffer and the static pairing; call once per step.
+
+    fuse_fn(feat_ref, feat_src, P_ref, P_src) -> anything; defaults to the Epipolar sampler passed in.
+    The pairing table is computed once on the host from the KRTs (they are per-camera constants in the
+    reference's datasets), so the per-step path contains no host synchronisation.
+    """
+
+    def __init__(self, KRT_all, sampler: Optional[Callable] = None, group=None, fuse_fn: Optional[Callable] = None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        KRT_all = torch.as_tensor(np.asarray(KRT_all), dtype=torch.float32)
+        if KRT_all.shape[0] != self.world:
+            raise ValueError("need one KRT per rank (got %d for world size %d)" % (KRT_all.shape[0], self.world))
+        self.src_of = source_view_table(KRT_all)
+        self.src = int(self.src_of[self.rank]) if self.world > 1 else 0
+        self.KRT_all = KRT_all
+        self.fuse_fn = fuse_fn if fuse_fn is not None else sampler
+        if self.fuse_fn is None:
+            raise ValueError("sampler or fuse_fn required")
+        self._buf = None
+
+    def gather(self, feat_view: torch.Tensor) -> torch.Tensor:
+        """all-gather of the per-view feature maps -> [V,B,C,H,W] (NVLink/NVSwitch under NCCL)."""
+        if self.world == 1:
+            return feat_view.unsqueeze(0)
+        shape = (self.world * feat_view.shape[0],) + tuple(feat_view.shape[1:])      # concatenated along dim 0
+        if self._buf is None or tuple(self._buf.shape) != shape or self._buf.device != feat_view.device:
+            self._buf = torch.empty(shape, device=feat_view.device, dtype=feat_view.dtype)
+        dist.all_gather_into_tensor(self._buf, feat_view.contiguous(), group=self.group)
+        return self._buf.view((self.world,) + tuple(feat_view.shape))
+
+    def __call__(self, feat_view: torch.Tensor):
+        B = feat_view.shape[0]
+        gathered = self.gather(feat_view)
+        feat_src = gathered[self.src]
+        dev = feat_view.device
+        P_ref = self.KRT_all[self.rank].to(dev).unsqueeze(0).expand(B, 3, 4).contiguous()
+        P_src = self.KRT_all[self.src].to(dev).unsqueeze(0).expand(B, 3, 4).contiguous()
+        return self.fuse_fn(feat_view, feat_src, P_ref, P_src)

@@ -74,8 +74,10 @@ def test_workspace_plan(lib):
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == m
     p.z_weight_folded = ctypes.addressof(buf)
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 2 * m
-    p.src_stride = (ctypes.c_int64 * 4)(256 * 4096, 1, 64 * 256, 256)      # channels_last: zero-copy
-    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == m
+    p.src_stride = (ctypes.c_int64 * 4)(256 * 4096, 1, 64 * 256, 256)      # channels_last
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 2 * m         # tensor-core kernel stages bf16 (hi, lo) planes
+    p.variant = _lib.EPI_VARIANT_WARP
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == m             # warp kernel reads channels_last in place
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
