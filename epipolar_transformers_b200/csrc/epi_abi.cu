@@ -26,7 +26,7 @@ bool src_is_channels_last(const EpiFusionParams *p) {
 }
 
 struct Plan {
-    size_t off_src = 0, off_prez = 0, total = 0;
+    size_t off_src = 0, off_prez = 0, off_counter = 0, total = 0;
     bool stage_src = false, has_z = false, tile = false;
 };
 
@@ -44,6 +44,7 @@ Plan make_plan(const EpiFusionParams *p) {
     size_t off = 0;
     if (pl.stage_src) { pl.off_src = off; off += align_up(map); }
     if (pl.has_z) { pl.off_prez = off; off += align_up(map); }
+    if (pl.tile) { pl.off_counter = off; off += 256; }
     pl.total = off;
     return pl;
 }
@@ -114,7 +115,8 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
     if (pl.tile) {
         __nv_bfloat16 *hi = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_src);
         __nv_bfloat16 *lo = hi + (size_t)p->N * p->C * p->H * p->W;
-        e = epi::launch_split_planes(p->feat_src, p->src_stride, hi, lo, p->N, p->C, p->H, p->W, st);
+        a.tile_counter = reinterpret_cast<int *>(ws + pl.off_counter);
+        e = epi::launch_split_planes(p->feat_src, p->src_stride, hi, lo, p->N, p->C, p->H, p->W, a.tile_counter, st);
         if (e != cudaSuccess) return fail(EPI_ECUDA, "operand staging launch failed: %s", cudaGetErrorString(e));
         launches++;
         a.src_hi = hi; a.src_lo = lo;

@@ -42,8 +42,9 @@ cudaError_t launch_nchw_to_nhwc(const float *src, const int64_t stride[4], float
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) split_planes_kernel(const float *__restrict__ src, int64_t sn, int64_t sc, int64_t sh,
                                                            int64_t sw, __nv_bfloat16 *__restrict__ hi,
-                                                           __nv_bfloat16 *__restrict__ lo, int C, int H, int W) {
+                                                           __nv_bfloat16 *__restrict__ lo, int C, int H, int W, int *zero_me) {
     __shared__ float tile[32][33];
+    if (zero_me && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) *zero_me = 0;   // tile scheduler counter
     const int HW = H * W;
     const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -76,9 +77,9 @@ __global__ void __launch_bounds__(256) split_planes_kernel(const float *__restri
 }
 
 cudaError_t launch_split_planes(const float *src, const int64_t stride[4], __nv_bfloat16 *hi, __nv_bfloat16 *lo, int N, int C,
-                                int H, int W, cudaStream_t st) {
+                                int H, int W, int *zero_me, cudaStream_t st) {
     dim3 grid((H * W + 31) / 32, (C + 31) / 32, N);
-    split_planes_kernel<<<grid, 256, 0, st>>>(src, stride[0], stride[1], stride[2], stride[3], hi, lo, C, H, W);
+    split_planes_kernel<<<grid, 256, 0, st>>>(src, stride[0], stride[1], stride[2], stride[3], hi, lo, C, H, W, zero_me);
     return cudaGetLastError();
 }
 

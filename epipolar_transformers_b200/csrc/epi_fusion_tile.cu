@@ -28,8 +28,9 @@ constexpr int TW = 8, TH = 4;     // tile of reference pixels (x, y)
 constexpr int TM = TW * TH;       // = 32 = MMA N
 constexpr int CHUNK = 128;        // union rows per MMA (M of GEMM1, K of GEMM2)
 constexpr int DMAX = 480;         // max union size handled in one pass (table row length)
-constexpr int NT = 512;
+constexpr int NT = 512;           // worker threads
 constexpr int NWARP = NT / 32;
+constexpr int NT_ALL = NT + 32;   // + one warp that only issues tcgen05.mma (keeps the ~75-cycle/MMA issue off the workers' critical path)
 constexpr int MAXWORDS = 512;     // bitmap words: H*W <= 16384
 constexpr int MAXKPL = 4;         // samples per lane: K <= 128
 constexpr float FIX = 1073741824.0f;   // 2^30 fixed point for the β scatter
@@ -48,9 +49,12 @@ constexpr uint32_t OFF_MISC = OFF_ENDS + TM * 16;
 constexpr uint32_t SMEM_BYTES = OFF_MISC + 256;
 constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;                 // 1024-byte alignment slack
 
-constexpr uint32_t TMEM_COLS = 256;
-constexpr uint32_t TMEM_S = 0;       // 4 chunks x 32 columns
-constexpr uint32_t TMEM_O = 128;     // 2 channel halves x 32 columns
+// Each accumulator is 64 columns wide: [0,32) = A·B_hi (+ A_lo·B_hi), [32,64) = A_hi·B_lo — the B operand is the
+// (hi, lo) pair stacked along N, so hi·hi and hi·lo share one MMA (2 instead of 3 MMAs per K step).
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TMEM_S = 0;       // 4 chunks x 64 columns
+constexpr uint32_t TMEM_O = 256;     // 2 channel halves x 64 columns
+constexpr uint32_t PANEL_B2 = 8192;  // stacked B panel: 64 rows x 128 B (rows 0-31 hi, 32-63 lo)
 
 struct Misc {
     uint64_t bar_stage[2];
@@ -97,7 +101,7 @@ __device__ unsigned long long g_tile_timers[16];
 #define TMARK(slot) do { } while (0)
 #endif
 
-__global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs a) {
+__global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_tile_kernel(const FusionArgs a) {
     extern __shared__ uint8_t smem_raw[];
     // keep the shared address space visible to the compiler: offset arithmetic on the array, no integer casts
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -111,16 +115,15 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
 
     const int C = a.C, K = a.geom.K, H = a.geom.H, W = a.geom.W, HW = H * W;
     const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
-    const int n = blockIdx.x / (tiles_x * tiles_y);
-    const int trem = blockIdx.x % (tiles_x * tiles_y);
-    const int ty0 = (trem / tiles_x) * TH, tx0 = (trem % tiles_x) * TW;
+    const int total_tiles = a.N * tiles_x * tiles_y;
+    int n = 0, ty0 = 0, tx0 = 0;                    // current tile (persistent CTA, dynamic tile scheduler)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const bool worker = warp < NWARP;               // warp NWARP only issues MMAs (and joins the CTA barriers)
     const int nwords = (HW + 31) >> 5;
     const int NH = (C + 127) >> 7;                  // channel halves of 128
     const GeomCfg gc = a.geom;
     const float sl2 = a.softmax_scale * 1.4426950408889634f;
-    const __nv_bfloat16 *src_hi = a.src_hi + (size_t)n * HW * C;
-    const __nv_bfloat16 *src_lo = a.src_lo + (size_t)n * HW * C;
+    const __nv_bfloat16 *src_hi = a.src_hi, *src_lo = a.src_lo;
     // tile pixel i -> (y, x), flattened index, validity
     auto pix_y = [&](int i) { return ty0 + (i >> 3); };
     auto pix_x = [&](int i) { return tx0 + (i & 7); };
@@ -131,13 +134,31 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
     if (tid == 32) {
         mbar_init(&ms.bar_stage[0], 1); mbar_init(&ms.bar_stage[1], 1); mbar_init(&ms.bar_all, 1);
         mbar_fence_init();
-        ms.sp = 1; ms.stack[0] = 0 | (TM << 8);
-        if (!a.locs_in) pair_geom_from_krt(a.P_ref + 12 * n, a.P_src + 12 * n, ms.geom);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = ms.tmem_base;
+    uint32_t n_stage = 0;      // stages issued so far (buffer = n_stage & 1), CTA-uniform
+    uint32_t n_all = 0;        // completions requested on bar_all
+    int cur_n = -1;
+#ifdef EPI_TILE_TIMERS
+    long long t_prev = clock64();
+#endif
+
+  for (int tile = blockIdx.x; tile < total_tiles;) {
+    {
+        n = tile / (tiles_x * tiles_y);
+        const int trem = tile % (tiles_x * tiles_y);
+        ty0 = (trem / tiles_x) * TH; tx0 = (trem % tiles_x) * TW;
+        src_hi = a.src_hi + (size_t)n * HW * C; src_lo = a.src_lo + (size_t)n * HW * C;
+    }
+    if (tid == 32) {
+        ms.sp = 1; ms.stack[0] = 0 | (TM << 8);
+        if (!a.locs_in && n != cur_n) pair_geom_from_krt(a.P_ref + 12 * n, a.P_src + 12 * n, ms.geom);
+    }
+    cur_n = n;
+    __syncthreads();
     if (tid < TM) {
         float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
         if (pix_ok(tid) && !a.locs_in)
@@ -160,12 +181,6 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
     };
     auto rank_of = [&](int pix) { return (int)(prefix[pix >> 5] + __popc(bitmap[pix >> 5] & ((1u << (pix & 31)) - 1u))); };
 
-#ifdef EPI_TILE_TIMERS
-    long long t_prev = clock64();
-#endif
-    uint32_t n_stage = 0;      // stages issued so far (buffer = n_stage & 1), CTA-uniform
-    uint32_t n_all = 0;        // completions requested on bar_all
-
     // ---------------- groups of pixels whose union of taps fits DMAX ----------------
     while (true) {
         __syncthreads();
@@ -177,7 +192,7 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
         if (tid < nwords) bitmap[tid] = 0u;
         __syncthreads();
         // mark every in-bounds tap of every sample of the group's pixels: warp <-> pixel, lane <-> sample
-        for (int i = g0 + warp; i < g0 + gn; i += NWARP) {
+        for (int i = g0 + warp; worker && i < g0 + gn; i += NWARP) {
             if (!pix_ok(i)) continue;
             for (int k = lane; k < K; k += 32) {
                 float gx, gy;
@@ -200,7 +215,7 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
             int incl = v;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-            if (lane == 31) ms.warp_tot[warp] = incl;
+            if (lane == 31 && worker) ms.warp_tot[warp] = incl;
             __syncthreads();
             int base = 0;
             for (int w = 0; w < warp; w++) base += ms.warp_tot[w];
@@ -233,7 +248,7 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
             const bool ok = i >= g0 && i < g0 + gn && pix_ok(i);
             const float *rb = a.feat_ref + (int64_t)n * a.ref_stride[0] + (int64_t)pix_y(i) * a.ref_stride[2] + (int64_t)pix_x(i) * a.ref_stride[3];
             const int64_t sc = a.ref_stride[1];
-            for (int cg = warp; cg < NH * 16; cg += NWARP) {      // groups of 8 channels
+            for (int cg = warp; worker && cg < NH * 16; cg += NWARP) {      // groups of 8 channels
                 float f[8];
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
@@ -242,9 +257,9 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
                 }
                 uint4 hi, lo;
                 split8(f, hi, lo);
-                const uint32_t off = (cg >> 3) * PANEL_B + i * 128u + (((cg & 7) ^ (i & 7)) << 4);
+                const uint32_t off = (cg >> 3) * PANEL_B2 + i * 128u + (((cg & 7) ^ (i & 7)) << 4);
                 *reinterpret_cast<uint4 *>(qb + off) = hi;
-                *reinterpret_cast<uint4 *>(qb + 16384 + off) = lo;
+                *reinterpret_cast<uint4 *>(qb + 4096 + off) = lo;
             }
         }
         __syncthreads();      // idx + Q visible
@@ -285,38 +300,43 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
         };
 
         // ---------------- phase A: S = F·Qᵀ ----------------
-        {
+        if (worker) {
             uint4 v[8];
             if (n_st > 0) gather_load(v, 0, 0);
             for (int st = 0; st < n_st; st++) {
-                const int c = st / NH, h = st % NH;
                 uint8_t *stage = acquire_stage();
                 gather_store(stage, v);
                 if (st + 1 < n_st) gather_load(v, (st + 1) / NH, (st + 1) % NH);
                 fence_proxy_async_smem();
                 tc_fence_before();
                 __syncthreads();
+                n_stage++;
+            }
+        } else {
+            for (int st = 0; st < n_st; st++) {
+                const int c = st / NH, h = st % NH;
+                __syncthreads();                                   // stage st is in shared memory
                 tc_fence_after();
-                if (tid == 0) {
-                    const uint32_t idesc = make_idesc_bf16(128, TM, 0, 0);
-                    const uint32_t sa = smem_u32(stage), sq = smem_u32(qb);
-                    const uint32_t dst = tmem + TMEM_S + c * TM;
+                if (lane == 0) {
+                    const uint32_t idesc64 = make_idesc_bf16(128, 2 * TM, 0, 0), idesc32 = make_idesc_bf16(128, TM, 0, 0);
+                    const uint32_t sa = smem_u32(smem + OFF_STAGE + (n_stage & 1) * STAGE_BYTES), sq = smem_u32(qb);
+                    const uint32_t dst = tmem + TMEM_S + c * 2 * TM;
 #pragma unroll
                     for (int ks = 0; ks < 8; ks++) {
-                        const uint32_t ao = (ks >> 2) * PANEL_A + (ks & 3) * 32, bo = (h * 2 + (ks >> 2)) * PANEL_B + (ks & 3) * 32;
+                        const uint32_t ao = (ks >> 2) * PANEL_A + (ks & 3) * 32, bo = (h * 2 + (ks >> 2)) * PANEL_B2 + (ks & 3) * 32;
                         const uint64_t a_hi = make_smem_desc(sa + ao, 16, 1024), a_lo = make_smem_desc(sa + 32768 + ao, 16, 1024);
-                        const uint64_t b_hi = make_smem_desc(sq + bo, 16, 1024), b_lo = make_smem_desc(sq + 16384 + bo, 16, 1024);
-                        mma_bf16(dst, a_hi, b_hi, idesc, (h | ks) ? 1u : 0u);
-                        mma_bf16(dst, a_hi, b_lo, idesc, 1u);
-                        mma_bf16(dst, a_lo, b_hi, idesc, 1u);
+                        const uint64_t b = make_smem_desc(sq + bo, 16, 1024);
+                        mma_bf16(dst, a_hi, b, idesc64, (h | ks) ? 1u : 0u);      // [F_hi·Q_hi | F_hi·Q_lo]
+                        mma_bf16(dst, a_lo, b, idesc32, 1u);                      //  += F_lo·Q_hi (first 32 rows of the stacked panel)
                     }
                     mma_commit(&ms.bar_stage[n_stage & 1]);
                 }
+                __syncwarp();
                 n_stage++;
             }
         }
         if (nch > 0) {
-            if (tid == 0) mma_commit(&ms.bar_all);
+            if (tid == NT) mma_commit(&ms.bar_all);
             bounded_wait(&ms.bar_all, n_all & 1); n_all++;
         }
         tc_fence_after();
@@ -326,13 +346,14 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
         {
             const int c = warp >> 2;
             if (c < nch) {
-                float v[32];
-                tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_S + c * TM, v);
+                float v[32], v2[32];
+                tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_S + c * 2 * TM, v);
+                tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_S + c * 2 * TM + TM, v2);
                 tmem_ld_wait();
                 const int d = c * CHUNK + (warp & 3) * 32 + lane;
                 if (d < D) {
 #pragma unroll
-                    for (int i = 0; i < TM; i++) table[i * DMAX + d] = v[i];
+                    for (int i = 0; i < TM; i++) table[i * DMAX + d] = v[i] + v2[i];
                 }
             }
         }
@@ -342,7 +363,7 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
         TMARK(3);
         // ---------------- phase B2: interpolate scores, softmax over K, outputs, β scatter ----------------
         float *attn_tile = reinterpret_cast<float *>(qb);         // [K][32]; Q panels are dead now
-        for (int i = g0 + warp; i < g0 + gn; i += NWARP) {
+        for (int i = g0 + warp; worker && i < g0 + gn; i += NWARP) {
             if (!pix_ok(i)) continue;
             const int p = pix_y(i) * W + pix_x(i);
             float x[MAXKPL], gxs[MAXKPL], gys[MAXKPL];
@@ -423,7 +444,7 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
         TMARK(4);
         if (a.attn) {       // flush the attention tile: 8-pixel row segments
             float *ab = a.attn + (size_t)n * K * HW;
-            for (int e = tid; e < K * TM; e += NT) {
+            for (int e = tid; worker && e < K * TM; e += NT) {
                 const int i = e & 31, k = e >> 5;
                 if (i >= g0 && i < g0 + gn && pix_ok(i)) ab[(size_t)k * HW + pix_y(i) * W + pix_x(i)] = attn_tile[k * TM + i];
             }
@@ -432,7 +453,7 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
 
         TMARK(5);
         // ---------------- phase C: Oᵀ = Fᵀ·βᵀ ----------------
-        {
+        if (worker) {
             uint4 v[8];
             if (n_st > 0) gather_load(v, 0, 0);
             for (int st = 0; st < n_st; st++) {
@@ -453,34 +474,40 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
                     }
                     uint4 hi, lo;
                     split8(f, hi, lo);
-                    const uint32_t off = (dg >> 3) * PANEL_B + i * 128u + (((dg & 7) ^ (i & 7)) << 4);
+                    const uint32_t off = (dg >> 3) * PANEL_B2 + i * 128u + (((dg & 7) ^ (i & 7)) << 4);
                     *reinterpret_cast<uint4 *>(bb + off) = hi;
-                    *reinterpret_cast<uint4 *>(bb + 8192 + off) = lo;
+                    *reinterpret_cast<uint4 *>(bb + 4096 + off) = lo;
                 }
                 fence_proxy_async_smem();
                 tc_fence_before();
                 __syncthreads();
+                n_stage++;
+            }
+        } else {
+            for (int st = 0; st < n_st; st++) {
+                const int c = st / NH, h = st % NH;
+                __syncthreads();
                 tc_fence_after();
-                if (tid == 0) {
-                    const uint32_t idesc = make_idesc_bf16(128, TM, 1, 0);
-                    const uint32_t sa = smem_u32(stage), sb = smem_u32(bb);
-                    const uint32_t dst = tmem + TMEM_O + h * TM;
+                if (lane == 0) {
+                    const uint32_t idesc64 = make_idesc_bf16(128, 2 * TM, 1, 0), idesc32 = make_idesc_bf16(128, TM, 1, 0);
+                    const uint32_t sa = smem_u32(smem + OFF_STAGE + (n_stage & 1) * STAGE_BYTES), sb = smem_u32(qb + (c & 1) * 16384);
+                    const uint32_t dst = tmem + TMEM_O + h * 2 * TM;
 #pragma unroll
                     for (int ks = 0; ks < 8; ks++) {
-                        const uint32_t ao = ks * 2048, bo = (ks >> 2) * PANEL_B + (ks & 3) * 32;
+                        const uint32_t ao = ks * 2048, bo = (ks >> 2) * PANEL_B2 + (ks & 3) * 32;
                         const uint64_t a_hi = make_smem_desc(sa + ao, PANEL_A, 1024), a_lo = make_smem_desc(sa + 32768 + ao, PANEL_A, 1024);
-                        const uint64_t b_hi = make_smem_desc(sb + bo, 16, 1024), b_lo = make_smem_desc(sb + 8192 + bo, 16, 1024);
-                        mma_bf16(dst, a_hi, b_hi, idesc, (c | ks) ? 1u : 0u);
-                        mma_bf16(dst, a_hi, b_lo, idesc, 1u);
-                        mma_bf16(dst, a_lo, b_hi, idesc, 1u);
+                        const uint64_t b = make_smem_desc(sb + bo, 16, 1024);
+                        mma_bf16(dst, a_hi, b, idesc64, (c | ks) ? 1u : 0u);      // [Fᵀ_hi·β_hi | Fᵀ_hi·β_lo]
+                        mma_bf16(dst, a_lo, b, idesc32, 1u);                      //  += Fᵀ_lo·β_hi
                     }
                     mma_commit(&ms.bar_stage[n_stage & 1]);
                 }
+                __syncwarp();
                 n_stage++;
             }
         }
         if (nch > 0) {
-            if (tid == 0) mma_commit(&ms.bar_all);
+            if (tid == NT) mma_commit(&ms.bar_all);
             bounded_wait(&ms.bar_all, n_all & 1); n_all++;
         }
         tc_fence_after();
@@ -493,18 +520,19 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
             constexpr int OS = 260;
             const int h = warp >> 2;
             if (h < NH) {
-                float v[32];
-                tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_O + h * TM, v);
+                float v[32], v2[32];
+                tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_O + h * 2 * TM, v);
+                tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + TMEM_O + h * 2 * TM + TM, v2);
                 tmem_ld_wait();
                 const int ch = h * 128 + (warp & 3) * 32 + lane;
 #pragma unroll
-                for (int i = 0; i < TM; i++) o_tile[i * OS + ch] = nch ? v[i] : 0.f;     // nch==0: every sample masked, zero vectors
+                for (int i = 0; i < TM; i++) o_tile[i * OS + ch] = nch ? v[i] + v2[i] : 0.f;   // nch==0: every sample masked, zero vectors
             }
             tc_fence_before();
             __syncthreads();
             if (a.out_hi) {
                 // bf16 (hi, lo) planes [N][HW][C]: the A operand of the z-projection GEMM; one 16-byte store per lane
-                for (int i = g0 + warp; i < g0 + gn; i += NWARP) {
+                for (int i = g0 + warp; worker && i < g0 + gn; i += NWARP) {
                     if (!pix_ok(i) || lane * 8 >= C) continue;
                     float f[8];
                     *reinterpret_cast<float4 *>(f) = *reinterpret_cast<const float4 *>(o_tile + i * OS + lane * 8);
@@ -521,7 +549,7 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
                 const bool ok = i >= g0 && i < g0 + gn && pix_ok(i);
                 float *ob = a.out + (int64_t)n * a.out_stride[0] + (int64_t)pix_y(i) * a.out_stride[2] + (int64_t)pix_x(i) * a.out_stride[3];
                 const float *rb = a.feat_ref + (int64_t)n * a.ref_stride[0] + (int64_t)pix_y(i) * a.ref_stride[2] + (int64_t)pix_x(i) * a.ref_stride[3];
-                if (ok)
+                if (ok && worker)
                     for (int ch = warp; ch < C; ch += NWARP) {
                         float o = o_tile[i * OS + ch];
                         if (a.add_ref) o += __ldg(rb + ch * a.ref_stride[1]);
@@ -529,7 +557,7 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
                     }
             } else {
                 // channels-last: lane <-> channel
-                for (int i = g0 + warp; i < g0 + gn; i += NWARP) {
+                for (int i = g0 + warp; worker && i < g0 + gn; i += NWARP) {
                     if (!pix_ok(i)) continue;
                     float *ob = a.out + (int64_t)n * a.out_stride[0] + (int64_t)pix_y(i) * a.out_stride[2] + (int64_t)pix_x(i) * a.out_stride[3];
                     const float *rb = a.feat_ref + (int64_t)n * a.ref_stride[0] + (int64_t)pix_y(i) * a.ref_stride[2] + (int64_t)pix_x(i) * a.ref_stride[3];
@@ -547,6 +575,13 @@ __global__ void __launch_bounds__(NT, 1) epi_fusion_tile_kernel(const FusionArgs
         if (tid == 0) atomicAdd(&g_tile_timers[8], 1ull);
 #endif
     }
+    // next tile: dynamic (atomic counter zeroed by the operand-staging kernel) or static round-robin
+    __syncthreads();
+    if (tid == 0) ms.total = a.tile_counter ? (int)gridDim.x + atomicAdd(a.tile_counter, 1) : tile + (int)gridDim.x;
+    __syncthreads();
+    tile = ms.total;
+    __syncthreads();
+  }
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
@@ -564,10 +599,14 @@ bool fusion_tile_supported(const FusionArgs &a) {
 }
 
 cudaError_t launch_fusion_tile(const FusionArgs &a, cudaStream_t st) {
-    const int tiles = ((a.geom.W + TW - 1) / TW) * ((a.geom.H + TH - 1) / TH);
+    const int tiles = a.N * ((a.geom.W + TW - 1) / TW) * ((a.geom.H + TH - 1) / TH);
     cudaError_t e = cudaFuncSetAttribute(epi_fusion_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
     if (e != cudaSuccess) return e;
-    epi_fusion_tile_kernel<<<a.N * tiles, NT, SMEM_ALLOC, st>>>(a);
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int grid = a.tile_counter ? (tiles < sms ? tiles : sms) : tiles;     // one persistent CTA per SM
+    epi_fusion_tile_kernel<<<grid, NT_ALL, SMEM_ALLOC, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -19,6 +19,7 @@ struct FusionArgs {
     int N, C;
     float softmax_scale;
     int add_ref;
+    int *tile_counter;                        // zeroed by the staging kernel; dynamic tile scheduler of the tile kernel
     GeomCfg geom;
 };
 
@@ -49,7 +50,7 @@ cudaError_t launch_fusion_tile(const FusionArgs &a, cudaStream_t st);
 bool fusion_tile_supported(const FusionArgs &a);
 bool fusion_tile_shape_ok(int C, int H, int W, int K, bool has_locs_in);
 cudaError_t launch_split_planes(const float *src, const int64_t stride[4], __nv_bfloat16 *hi, __nv_bfloat16 *lo, int N, int C,
-                                int H, int W, cudaStream_t st);
+                                int H, int W, int *zero_me, cudaStream_t st);
 
 cudaError_t launch_nchw_to_nhwc(const float *src, const int64_t stride[4], float *dst, int N, int C, int H, int W, cudaStream_t st);
 cudaError_t launch_z_epilogue(const ZArgs &z, cudaStream_t st);

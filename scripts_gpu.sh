@@ -1,3 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 120 python tools/gpu_mma_bench.py > gpurun_out/mma_bench.log 2>&1; cat gpurun_out/mma_bench.log
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 300 python tools/gpu_timers.py 64 > gpurun_out/timers.log 2>&1
+timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_tile.json 2> gpurun_out/bench_tile.err
+tail -n 4 gpurun_out/pytest_gpu.log; cat gpurun_out/timers.log; cut -c1-250 gpurun_out/bench_tile.json; tail -n 3 gpurun_out/bench_tile.err

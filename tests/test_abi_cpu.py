@@ -71,11 +71,11 @@ def test_workspace_plan(lib):
     p.feat_src = ctypes.addressof(buf)
     p.src_stride = (ctypes.c_int64 * 4)(256 * 4096, 4096, 64, 1)           # NCHW: needs staging
     m = 4 * 256 * 64 * 64 * 4
-    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == m
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == m + 256       # + tile-scheduler counter
     p.z_weight_folded = ctypes.addressof(buf)
-    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 2 * m
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 2 * m + 256
     p.src_stride = (ctypes.c_int64 * 4)(256 * 4096, 1, 64 * 256, 256)      # channels_last
-    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 2 * m         # tensor-core kernel stages bf16 (hi, lo) planes
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 2 * m + 256   # tensor-core kernel stages bf16 (hi, lo) planes
     p.variant = _lib.EPI_VARIANT_WARP
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == m             # warp kernel reads channels_last in place
 

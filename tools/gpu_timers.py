@@ -26,3 +26,5 @@ tot = v[:8].sum()
 for nm, x in zip(names, v[:8]):
     print("%-20s %8.0f cyc/group  %5.1f%%" % (nm, x / groups, 100 * x / tot))
 print("total cyc/group %.0f  cyc/tile %.0f" % (tot / groups, tot / tiles))
+for nm, i in (("A: acquire wait", 9), ("A: gather_store (waits loads)", 10), ("A: gather_load issue", 11), ("A: fence+sync", 12), ("A: mma issue", 13), ("A: loop overhead", 14)):
+    print("%-32s %8.0f cyc/group" % (nm, v[i] / groups))
