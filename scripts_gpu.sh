@@ -1,6 +1,5 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
-timeout 300 python tools/gpu_timers.py 64 > gpurun_out/timers.log 2>&1
-timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_tile.json 2> gpurun_out/bench_tile.err
-tail -n 4 gpurun_out/pytest_gpu.log; cat gpurun_out/timers.log; cut -c1-250 gpurun_out/bench_tile.json; tail -n 3 gpurun_out/bench_tile.err
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "streamer" > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 400 python bench.py --steps 100 --warmup 10 --no-cpu-baseline > gpurun_out/bench_ours.json 2> gpurun_out/bench_ours.err
+tail -n 4 gpurun_out/pytest_gpu.log; python -c "import json;d=json.load(open('gpurun_out/bench_ours.json'));print(d['ms_per_step'], d['e2e'])"; tail -n 3 gpurun_out/bench_ours.err

@@ -227,3 +227,22 @@ def test_full_size_properties(shape):
     assert (attnz - 1.0 / K).abs().max().item() < 1e-7
     outz2 = epi.epipolar_fusion(torch.zeros_like(f1), 2 * f2, dev(P1), dev(P2), **kw)[0]
     assert (outz2 - 2 * outz).abs().max().item() < 1e-5
+
+
+def test_host_streamer_matches_direct_call():
+    """pinned-host front end (three-stream pipeline) returns exactly what the direct device call returns."""
+    name = "cfg1_ring"
+    cfg, f1, f2, P1, P2, _ = gc.build_inputs(name)
+    m = epi.Epipolar(cfg=cfg).cuda().eval()
+    with torch.no_grad():
+        out, corr, attn, _ = m(dev(f1), dev(f2), dev(P1), dev(P2))
+    hs = epi.HostStreamer(m, "cuda", depth=2)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    h = [pin(f1), pin(f2), pin(P1), pin(P2)]
+    outs = [(torch.empty_like(out, device="cpu").pin_memory(), torch.empty_like(attn, device="cpu").pin_memory(),
+             torch.empty_like(corr, device="cpu").pin_memory()) for _ in range(5)]
+    for o, a_, c in outs:
+        hs(h[0], h[1], h[2], h[3], o, a_, c)
+    hs.synchronize()
+    for o, a_, c in outs:
+        assert torch.equal(o, out.cpu()) and torch.equal(a_, attn.cpu()) and torch.equal(c, corr.cpu())
