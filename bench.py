@@ -203,7 +203,7 @@ def run_ours(args, wl):
     # cameras: `max(world,4)` views on a ring; single-GPU: pair v = (view v, nearest view), like the
     # H36M test-time batch.  Multi-GPU: rank r owns view r, N frames of it.
     V = max(world, 4) if world > 1 else N
-    KRT = syn.ring_cameras(V, 4 * H)
+    KRT = syn.ring_cameras(V, 4 * H)[:max(world, 1) if world > 1 else N]      # cameras that exist = the ranks
     src_of = syn.nearest_source(KRT)
     if world == 1:
         P_ref = torch.from_numpy(KRT.astype(np.float32)).to(dev)
