@@ -101,6 +101,7 @@ __device__ unsigned long long g_tile_timers[16];
 #define TMARK(slot) do { } while (0)
 #endif
 
+template <int KPL>
 __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_tile_kernel(const FusionArgs a) {
     extern __shared__ uint8_t smem_raw[];
     // keep the shared address space visible to the compiler: offset arithmetic on the array, no integer casts
@@ -191,20 +192,24 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_tile_kernel(const Fusion
         if (tid == 0) ms.sp--;
         if (tid < nwords) bitmap[tid] = 0u;
         __syncthreads();
-        // mark every in-bounds tap of every sample of the group's pixels: warp <-> pixel, lane <-> sample
-        for (int i = g0 + warp; worker && i < g0 + gn; i += NWARP) {
-            if (!pix_ok(i)) continue;
-            for (int k = lane; k < K; k += 32) {
-                float gx, gy;
-                sample_loc(i, k, gx, gy);
-                const Taps t = make_taps(gx, gy, H, W, gc.align);
-                if (t.any) {
+        // mark every in-bounds tap of every sample of the group's pixels.  lane <-> pixel, warp <-> sample
+        // (k = warp, warp+16, ...): the 32 lanes of one atomic belong to 32 different epipolar lines, so they
+        // spread over several bitmap words instead of piling onto the one word a single line crosses.
+        if (worker) {
+            const int i = lane;
+            if (i >= g0 && i < g0 + gn && pix_ok(i)) {
+                for (int k = warp; k < K; k += NWARP) {
+                    float gx, gy;
+                    sample_loc(i, k, gx, gy);
+                    const Taps t = make_taps(gx, gy, H, W, gc.align);
+                    if (t.any) {
 #pragma unroll
-                    for (int tp = 0; tp < 4; tp++)
-                        if (t.w[tp] != 0.f) {
-                            const int pix = (t.y0 + (tp >> 1)) * W + t.x0 + (tp & 1);
-                            atomicOr(&bitmap[pix >> 5], 1u << (pix & 31));
-                        }
+                        for (int tp = 0; tp < 4; tp++)
+                            if (t.w[tp] != 0.f) {
+                                const int pix = (t.y0 + (tp >> 1)) * W + t.x0 + (tp & 1);
+                                atomicOr(&bitmap[pix >> 5], 1u << (pix & 31));
+                            }
+                    }
                 }
             }
         }
@@ -248,18 +253,28 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_tile_kernel(const Fusion
             const bool ok = i >= g0 && i < g0 + gn && pix_ok(i);
             const float *rb = a.feat_ref + (int64_t)n * a.ref_stride[0] + (int64_t)pix_y(i) * a.ref_stride[2] + (int64_t)pix_x(i) * a.ref_stride[3];
             const int64_t sc = a.ref_stride[1];
-            for (int cg = warp; worker && cg < NH * 16; cg += NWARP) {      // groups of 8 channels
-                float f[8];
+            if (worker) {
+                float f[2][8];
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int c = cg * 8 + u;
-                    f[u] = (ok && c < C) ? __ldg(rb + c * sc) : 0.f;
+                for (int it = 0; it < 2; it++) {                   // groups of 8 channels: cg = warp, warp + 16
+                    const int cg = warp + it * NWARP;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int c = cg * 8 + u;
+                        f[it][u] = (ok && cg < NH * 16 && c < C) ? __ldg(rb + c * sc) : 0.f;
+                    }
                 }
-                uint4 hi, lo;
-                split8(f, hi, lo);
-                const uint32_t off = (cg >> 3) * PANEL_B2 + i * 128u + (((cg & 7) ^ (i & 7)) << 4);
-                *reinterpret_cast<uint4 *>(qb + off) = hi;
-                *reinterpret_cast<uint4 *>(qb + 4096 + off) = lo;
+#pragma unroll
+                for (int it = 0; it < 2; it++) {
+                    const int cg = warp + it * NWARP;
+                    if (cg < NH * 16) {
+                        uint4 hi, lo;
+                        split8(f[it], hi, lo);
+                        const uint32_t off = (cg >> 3) * PANEL_B2 + i * 128u + (((cg & 7) ^ (i & 7)) << 4);
+                        *reinterpret_cast<uint4 *>(qb + off) = hi;
+                        *reinterpret_cast<uint4 *>(qb + 4096 + off) = lo;
+                    }
+                }
             }
         }
         __syncthreads();      // idx + Q visible
@@ -363,79 +378,107 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_tile_kernel(const Fusion
         TMARK(3);
         // ---------------- phase B2: interpolate scores, softmax over K, outputs, β scatter ----------------
         float *attn_tile = reinterpret_cast<float *>(qb);         // [K][32]; Q panels are dead now
-        for (int i = g0 + warp; worker && i < g0 + gn; i += NWARP) {
-            if (!pix_ok(i)) continue;
-            const int p = pix_y(i) * W + pix_x(i);
-            float x[MAXKPL], gxs[MAXKPL], gys[MAXKPL];
-            float mx = -INFINITY;
+        if (worker) {
+            // Each warp owns up to two pixels (i0, i0+16) and runs them interleaved for instruction-level
+            // parallelism; lane <-> sample.  Tap ranks and weights are kept in registers for the β scatter.
+            constexpr int PW = TM / NWARP;                         // 2
+            float x[PW][KPL], gxs[PW][KPL], gys[PW][KPL], tw[PW][KPL][4];
+            uint32_t rk[PW][KPL][2];                            // 4 ranks, packed 2 x u16
+            bool act[PW];
+            float mx[PW];
 #pragma unroll
-            for (int j = 0; j < MAXKPL; j++) {
-                const int k = j * 32 + lane;
-                x[j] = -INFINITY; gxs[j] = 0.f; gys[j] = 0.f;
-                if (k < K) {
-                    float gx, gy;
-                    sample_loc(i, k, gx, gy);
-                    gxs[j] = gx; gys[j] = gy;
-                    if (a.locs_out) reinterpret_cast<float2 *>(a.locs_out)[((size_t)k * a.N + n) * HW + p] = make_float2(gx, gy);
-                    const Taps t = make_taps(gx, gy, H, W, gc.align);
-                    float sim = 0.f;
-                    if (t.any) {
+            for (int u = 0; u < PW; u++) {
+                const int i = g0 + warp + u * NWARP;
+                act[u] = i < g0 + gn && pix_ok(i);
+                mx[u] = -INFINITY;
 #pragma unroll
-                        for (int tp = 0; tp < 4; tp++)
-                            if (t.w[tp] != 0.f)
-                                sim = fmaf(t.w[tp], table[i * DMAX + rank_of((t.y0 + (tp >> 1)) * W + t.x0 + (tp & 1))], sim);
+                for (int j = 0; j < KPL; j++) {
+                    const int k = j * 32 + lane;
+                    x[u][j] = -INFINITY; gxs[u][j] = 0.f; gys[u][j] = 0.f; rk[u][j][0] = rk[u][j][1] = 0u;
+#pragma unroll
+                    for (int tp = 0; tp < 4; tp++) tw[u][j][tp] = 0.f;
+                    if (act[u] && k < K) {
+                        float gx, gy;
+                        sample_loc(i, k, gx, gy);
+                        gxs[u][j] = gx; gys[u][j] = gy;
+                        if (a.locs_out)
+                            reinterpret_cast<float2 *>(a.locs_out)[((size_t)k * a.N + n) * HW + pix_y(i) * W + pix_x(i)] = make_float2(gx, gy);
+                        const Taps t = make_taps(gx, gy, H, W, gc.align);
+                        float sim = 0.f;
+                        if (t.any) {
+                            uint32_t r[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                            for (int tp = 0; tp < 4; tp++)
+                                if (t.w[tp] != 0.f) {
+                                    r[tp] = (uint32_t)rank_of((t.y0 + (tp >> 1)) * W + t.x0 + (tp & 1));
+                                    tw[u][j][tp] = t.w[tp];
+                                    sim = fmaf(t.w[tp], table[i * DMAX + r[tp]], sim);
+                                }
+                            rk[u][j][0] = r[0] | (r[1] << 16); rk[u][j][1] = r[2] | (r[3] << 16);
+                        }
+                        if (sim == 0.f) sim = kMasked;                      // epipolar.py:298
+                        x[u][j] = sim * sl2;
+                        mx[u] = fmaxf(mx[u], x[u][j]);
                     }
-                    if (sim == 0.f) sim = kMasked;                      // epipolar.py:298
-                    x[j] = sim * sl2;
-                    mx = fmaxf(mx, x[j]);
                 }
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-            float sum = 0.f;
+            for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-            for (int j = 0; j < MAXKPL; j++) { x[j] = (j * 32 + lane < K) ? exp2f(x[j] - mx) : 0.f; sum += x[j]; }
+                for (int u = 0; u < PW; u++) mx[u] = fmaxf(mx[u], __shfl_xor_sync(0xffffffffu, mx[u], o));
+            float sum[PW];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            const float inv = 1.f / sum;
-            float best_v = -1.f, best_gx = 0.f, best_gy = 0.f;
-            int best_k = 0x7fffffff;
+            for (int u = 0; u < PW; u++) {
+                sum[u] = 0.f;
 #pragma unroll
-            for (int j = 0; j < MAXKPL; j++) {
-                const int k = j * 32 + lane;
-                x[j] *= inv;
-                if (k < K) {
-                    if (a.attn) attn_tile[k * TM + i] = x[j];
-                    if (x[j] > best_v) { best_v = x[j]; best_k = k; best_gx = gxs[j]; best_gy = gys[j]; }
-                }
+                for (int j = 0; j < KPL; j++) { x[u][j] = (act[u] && j * 32 + lane < K) ? exp2f(x[u][j] - mx[u]) : 0.f; sum[u] += x[u][j]; }
             }
-            if (a.corr_pos) {
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
-                    const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
-                    const float ogx = __shfl_xor_sync(0xffffffffu, best_gx, o), ogy = __shfl_xor_sync(0xffffffffu, best_gy, o);
-                    if (ov > best_v || (ov == best_v && ok < best_k)) { best_v = ov; best_k = ok; best_gx = ogx; best_gy = ogy; }
+            for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                for (int u = 0; u < PW; u++) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+#pragma unroll
+            for (int u = 0; u < PW; u++) {
+                if (!act[u]) continue;                              // warp-uniform
+                const int i = g0 + warp + u * NWARP;
+                const float inv = 1.f / sum[u];
+                float best_v = -1.f, best_gx = 0.f, best_gy = 0.f;
+                int best_k = 0x7fffffff;
+#pragma unroll
+                for (int j = 0; j < KPL; j++) {
+                    const int k = j * 32 + lane;
+                    x[u][j] *= inv;
+                    if (k < K) {
+                        if (a.attn) attn_tile[k * TM + i] = x[u][j];
+                        if (x[u][j] > best_v) { best_v = x[u][j]; best_k = k; best_gx = gxs[u][j]; best_gy = gys[u][j]; }
+                    }
                 }
-                if (lane == 0)
-                    reinterpret_cast<float2 *>(a.corr_pos)[(size_t)n * HW + p] =
-                        make_float2(grid2corr(best_gx, W, gc.correct), grid2corr(best_gy, H, gc.correct));
-            }
-            // β row: zero, then deterministic fixed-point scatter of a_k·w_kt
-            __syncwarp();
-            int *trow = reinterpret_cast<int *>(table + i * DMAX);
-            for (int d = lane; d < D; d += 32) trow[d] = 0;
-            __syncwarp();
+                if (a.corr_pos) {
 #pragma unroll
-            for (int j = 0; j < MAXKPL; j++) {
-                const int k = j * 32 + lane;
-                if (k < K) {
-                    const Taps t = make_taps(gxs[j], gys[j], H, W, gc.align);
-                    if (t.any) {
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+                        const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+                        const float ogx = __shfl_xor_sync(0xffffffffu, best_gx, o), ogy = __shfl_xor_sync(0xffffffffu, best_gy, o);
+                        if (ov > best_v || (ov == best_v && ok < best_k)) { best_v = ov; best_k = ok; best_gx = ogx; best_gy = ogy; }
+                    }
+                    if (lane == 0)
+                        reinterpret_cast<float2 *>(a.corr_pos)[(size_t)n * HW + pix_y(i) * W + pix_x(i)] =
+                            make_float2(grid2corr(best_gx, W, gc.correct), grid2corr(best_gy, H, gc.correct));
+                }
+                // β row: zero, then deterministic fixed-point scatter of a_k·w_kt
+                int *trow = reinterpret_cast<int *>(table + i * DMAX);
+                __syncwarp();
+                for (int d = lane; d < D; d += 32) trow[d] = 0;
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < KPL; j++) {
+                    if (j * 32 + lane < K) {
 #pragma unroll
                         for (int tp = 0; tp < 4; tp++)
-                            if (t.w[tp] != 0.f)
-                                atomicAdd(&trow[rank_of((t.y0 + (tp >> 1)) * W + t.x0 + (tp & 1))], __float2int_rn(x[j] * t.w[tp] * FIX));
+                            if (tw[u][j][tp] != 0.f) {
+                                const uint32_t r = (rk[u][j][tp >> 1] >> ((tp & 1) * 16)) & 0xffffu;
+                                atomicAdd(&trow[r], __float2int_rn(x[u][j] * tw[u][j][tp] * FIX));
+                            }
                     }
                 }
             }
@@ -600,13 +643,15 @@ bool fusion_tile_supported(const FusionArgs &a) {
 
 cudaError_t launch_fusion_tile(const FusionArgs &a, cudaStream_t st) {
     const int tiles = a.N * ((a.geom.W + TW - 1) / TW) * ((a.geom.H + TH - 1) / TH);
-    cudaError_t e = cudaFuncSetAttribute(epi_fusion_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
+    const int kpl = (a.geom.K + 31) / 32;
+    auto kern = kpl <= 1 ? epi_fusion_tile_kernel<1> : (kpl <= 2 ? epi_fusion_tile_kernel<2> : epi_fusion_tile_kernel<4>);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
     if (e != cudaSuccess) return e;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int grid = a.tile_counter ? (tiles < sms ? tiles : sms) : tiles;     // one persistent CTA per SM
-    epi_fusion_tile_kernel<<<grid, NT_ALL, SMEM_ALLOC, st>>>(a);
+    kern<<<grid, NT_ALL, SMEM_ALLOC, st>>>(a);
     return cudaGetLastError();
 }
 
