@@ -222,11 +222,23 @@ def run_ours(args, wl):
     gathered_flat = torch.empty((world * N, C, H, W), device=dev) if world > 1 else None
     gathered = gathered_flat.view(world, N, C, H, W) if world > 1 else None
 
+    recv_buf = torch.empty((N, C, H, W), device=dev) if world > 1 else None
+    consumers = [r for r in range(world) if int(src_of[r]) == rank] if world > 1 else []
+
+    def exchange(f_ref):
+        """the path's only exchange step: this rank needs the feature map of its source view"""
+        if args.exchange == "allgather":
+            dist.all_gather_into_tensor(gathered_flat, f_ref)           # every map to every rank (BASELINE config 4 / MULTITEST)
+            return gathered[src_of[rank]]
+        ops = [dist.P2POp(dist.irecv, recv_buf, int(src_of[rank]))] + [dist.P2POp(dist.isend, f_ref, r) for r in consumers]
+        for req in dist.batch_isend_irecv(ops):                         # NCCL send/recv permutation over NVLink
+            req.wait()
+        return recv_buf
+
     def step(i):
         f_ref = refs[i % n_sets]
         if world > 1:
-            dist.all_gather_into_tensor(gathered_flat, f_ref)           # exchange per-view feature maps (NVLink)
-            f_src = gathered[src_of[rank]]
+            f_src = exchange(f_ref)
         else:
             f_src = srcs[i % n_sets]
         with torch.no_grad():
@@ -289,8 +301,7 @@ def run_ours(args, wl):
             streamer(h_ref[i % 2], h_src[i % 2], h_P1, h_P2, h_out, h_attn, h_corr)
             return
         d_ref = h_ref[i % 2].to(dev, non_blocking=True)
-        dist.all_gather_into_tensor(gathered_flat, d_ref)
-        d_src = gathered[src_of[rank]]
+        d_src = exchange(d_ref)
         d_P1 = h_P1.to(dev, non_blocking=True); d_P2 = h_P2.to(dev, non_blocking=True)
         with torch.no_grad():
             o, c, a, _ = model(d_ref, d_src, d_P1, d_P2)
@@ -340,12 +351,12 @@ def run_ours(args, wl):
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "pairs_per_gpu": N, "C": C, "feat_hw": [H, W], "K": K,
-                       "parallelism": "1 view per GPU, NCCL all-gather of feature maps" if world > 1 else "single GPU",
+                       "parallelism": ("1 view per GPU, NCCL %s of per-view feature maps" % ("all-gather" if args.exchange == "allgather" else "send/recv (each rank receives only its source view)")) if world > 1 else "single GPU",
                        "l2": "rotating %d input sets (%.0f MB > 126 MB L2), no reuse between consecutive steps" % (n_sets, n_sets * set_bytes / 1e6),
                        "outputs": "finalout + attn + corr_pos", "variant": args.variant},
             "clocks": clocks,
             "e2e": {"value": world * N / (e2e_ms * 1e-3), "unit": "views/s", "ms_per_step": e2e_ms, "wall_ms_per_step": e2e_wall_ms,
-                    "how": "pinned host buffers -> HostStreamer(Epipolar) -> pinned host buffers; H2D of step i+1 overlaps kernels + D2H of step i (2 streams)" if world == 1 else "pinned host -> device, all-gather, Epipolar, device -> pinned host, one stream",
+                    "how": "pinned host buffers -> HostStreamer(Epipolar) -> pinned host buffers; H2D of step i+1 overlaps kernels + D2H of step i (2 streams)" if world == 1 else "pinned host -> device, exchange, Epipolar, device -> pinned host, one stream",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "fused epipolar attention kernel (geometry+taps+softmax+AV)",
@@ -369,6 +380,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default="auto", choices=["auto", "warp", "tile"])
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"], help="multi-GPU exchange of per-view feature maps")
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -63,6 +63,7 @@ struct Misc {
     int stack[16];
     int sp;
     int total;
+    int next_tile;
     int warp_tot[NWARP];
     PairGeom geom;
 };
@@ -158,6 +159,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_tile_kernel(const Fusion
         ms.sp = 1; ms.stack[0] = 0 | (TM << 8);
         if (!a.locs_in && n != cur_n) pair_geom_from_krt(a.P_ref + 12 * n, a.P_src + 12 * n, ms.geom);
     }
+    if (tid == 64)      // claim the next tile now; its index is consumed after this tile (hides the atomic's latency)
+        ms.next_tile = a.tile_counter ? (int)gridDim.x + atomicAdd(a.tile_counter, 1) : tile + (int)gridDim.x;
     cur_n = n;
     __syncthreads();
     if (tid < TM) {
@@ -620,9 +623,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_tile_kernel(const Fusion
     }
     // next tile: dynamic (atomic counter zeroed by the operand-staging kernel) or static round-robin
     __syncthreads();
-    if (tid == 0) ms.total = a.tile_counter ? (int)gridDim.x + atomicAdd(a.tile_counter, 1) : tile + (int)gridDim.x;
-    __syncthreads();
-    tile = ms.total;
+    tile = ms.next_tile;
     __syncthreads();
   }
     __syncthreads();

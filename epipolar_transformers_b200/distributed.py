@@ -34,7 +34,14 @@ class ViewParallelFusion:
     reference's datasets), so the per-step path contains no host synchronisation.
     """
 
-    def __init__(self, KRT_all, sampler: Optional[Callable] = None, group=None, fuse_fn: Optional[Callable] = None):
+    def __init__(self, KRT_all, sampler: Optional[Callable] = None, group=None, fuse_fn: Optional[Callable] = None,
+                 exchange: str = "p2p"):
+        """exchange='p2p': every rank receives only the map of its source view (send/recv permutation, (V-1)x
+        fewer bytes than an all-gather); exchange='allgather': every rank receives all maps (what BASELINE
+        config 4 names and what MULTITEST-style all-neighbour fusion needs)."""
+        if exchange not in ("p2p", "allgather"):
+            raise ValueError(exchange)
+        self.exchange = exchange
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -43,6 +50,8 @@ class ViewParallelFusion:
             raise ValueError("need one KRT per rank (got %d for world size %d)" % (KRT_all.shape[0], self.world))
         self.src_of = source_view_table(KRT_all)
         self.src = int(self.src_of[self.rank]) if self.world > 1 else 0
+        self.consumers = [r for r in range(self.world) if int(self.src_of[r]) == self.rank and r != self.rank] if self.world > 1 else []
+        self._recv = None
         self.KRT_all = KRT_all
         self.fuse_fn = fuse_fn if fuse_fn is not None else sampler
         if self.fuse_fn is None:
@@ -59,10 +68,22 @@ class ViewParallelFusion:
         dist.all_gather_into_tensor(self._buf, feat_view.contiguous(), group=self.group)
         return self._buf.view((self.world,) + tuple(feat_view.shape))
 
+    def fetch_source(self, feat_view: torch.Tensor) -> torch.Tensor:
+        """Point-to-point exchange: receive the source view's map, send ours to the ranks that fuse against it."""
+        if self.world == 1:
+            return feat_view
+        if self._recv is None or self._recv.shape != feat_view.shape or self._recv.device != feat_view.device:
+            self._recv = torch.empty_like(feat_view)
+        send = feat_view.contiguous()
+        ops = [dist.P2POp(dist.irecv, self._recv, self.src, group=self.group)]
+        ops += [dist.P2POp(dist.isend, send, r, group=self.group) for r in self.consumers]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+        return self._recv
+
     def __call__(self, feat_view: torch.Tensor):
         B = feat_view.shape[0]
-        gathered = self.gather(feat_view)
-        feat_src = gathered[self.src]
+        feat_src = self.fetch_source(feat_view) if self.exchange == "p2p" else self.gather(feat_view)[self.src]
         dev = feat_view.device
         P_ref = self.KRT_all[self.rank].to(dev).unsqueeze(0).expand(B, 3, 4).contiguous()
         P_src = self.KRT_all[self.src].to(dev).unsqueeze(0).expand(B, 3, 4).contiguous()

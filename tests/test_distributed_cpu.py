@@ -31,8 +31,11 @@ def _worker(rank, world, port, out):
             seen["P_ref"] = P_ref[0].numpy().copy(); seen["P_src"] = P_src[0].numpy().copy()
             return f_ref + f_src
 
-        vp = ViewParallelFusion(KRT, fuse_fn=fake_fuse)
+        vp = ViewParallelFusion(KRT, fuse_fn=fake_fuse, exchange="allgather")
         y = vp(feat)
+        vp2 = ViewParallelFusion(KRT, fuse_fn=fake_fuse, exchange="p2p")
+        y2 = vp2(feat)
+        assert torch.equal(y, y2)                                       # both exchange modes deliver the same source map
         src = int(source_view_table(KRT)[rank])
         assert vp.src == src and src != rank
         assert seen["src_val"] == float(src + 1)                       # fused against the gathered map of view src(v)

@@ -246,3 +246,30 @@ def test_host_streamer_matches_direct_call():
     hs.synchronize()
     for o, a_, c in outs:
         assert torch.equal(o, out.cpu()) and torch.equal(a_, attn.cpu()) and torch.equal(c, corr.cpu())
+
+
+SWEEP = [  # (N, C, H, W, K)   BASELINE config 5 corners + map sizes on both sides of the tensor-core kernel's limits
+    (1, 64, 64, 64, 16), (1, 128, 64, 64, 32), (1, 256, 64, 64, 128), (1, 512, 32, 32, 64),   # C=512 -> warp kernel
+    (1, 64, 128, 128, 32),                                                                       # H*W = 16384: largest tile-kernel map
+    (1, 32, 160, 96, 16),                                                                        # non-square
+    (1, 16, 144, 144, 16),                                                                       # H*W > 16384 -> warp kernel
+    (2, 40, 24, 40, 48),                                                                         # C % 32 != 0, partial tiles
+    (1, 64, 256, 256, 16),                                                                       # literal 256x256 feature-map reading
+]
+
+
+@pytest.mark.parametrize("shape", SWEEP)
+def test_sweep_shapes_vs_oracle(shape):
+    """K/C/map-size sweep (BASELINE config 5): default kernel selection, end to end vs the C oracle."""
+    N, C, H, W, K = shape
+    from epipolar_transformers_b200 import synthetic as syn
+    cfg = epi.make_cfg(KEYPOINT=dict(HEATMAP_SIZE=(H, W), NFEATS=C), EPIPOLAR=dict(SAMPLESIZE=K, USE_CORRECT_NORMALIZE=True))
+    P1, P2 = syn.pairs_from_ring(max(N, 2), 4 * max(H, W), seed=K)
+    P1, P2 = P1[:N].astype(np.float32), P2[:N].astype(np.float32)
+    f1 = syn.features(N, C, H, W, "randn", 5); f2 = syn.features(N, C, H, W, "randn", 6)
+    out, corr, attn, locs = epi.epipolar_fusion(dev(f1), dev(f2), dev(P1), dev(P2), K=K, correct_normalize=True, want_locs=True)
+    torch.cuda.synchronize()
+    o = c_oracle.forward(cfg, f1, f2, P1, P2, locs=locs.cpu().numpy())
+    assert rel_max(out.cpu().numpy(), o["out"]) < TOL
+    assert rel_max(attn.cpu().numpy(), o["attn"]) < TOL
+    assert corr_agree(corr.cpu().numpy(), o["corr_pos"]) > 0.99
