@@ -188,6 +188,7 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("EPI_NCCL_DEBUG", "WARN")       # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -217,7 +218,17 @@ def run_ours(args, wl):
     n_sets = max(2, int(np.ceil(3.0 * L2_BYTES / set_bytes)))
     n_sets = min(n_sets, 24)
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
-    refs = [torch.relu(torch.randn(N, C, H, W, device=dev, generator=gen)) for _ in range(n_sets)]
+    symm_hdls = None
+    if world > 1 and args.exchange == "peer":
+        import torch.distributed._symmetric_memory as symm
+        refs, symm_hdls = [], []
+        for _ in range(n_sets):                       # the "backbone output" buffers live in peer-mapped memory
+            t = symm.empty(N, C, H, W, dtype=torch.float32, device=dev)
+            symm_hdls.append(symm.rendezvous(t, dist.group.WORLD))
+            t.copy_(torch.relu(torch.randn(N, C, H, W, device=dev, generator=gen)))
+            refs.append(t)
+    else:
+        refs = [torch.relu(torch.randn(N, C, H, W, device=dev, generator=gen)) for _ in range(n_sets)]
     srcs = [torch.relu(torch.randn(N, C, H, W, device=dev, generator=gen)) for _ in range(n_sets)]
     gathered_flat = torch.empty((world * N, C, H, W), device=dev) if world > 1 else None
     gathered = gathered_flat.view(world, N, C, H, W) if world > 1 else None
@@ -225,8 +236,12 @@ def run_ours(args, wl):
     recv_buf = torch.empty((N, C, H, W), device=dev) if world > 1 else None
     consumers = [r for r in range(world) if int(src_of[r]) == rank] if world > 1 else []
 
-    def exchange(f_ref):
+    def exchange(f_ref, i=0):
         """the path's only exchange step: this rank needs the feature map of its source view"""
+        if args.exchange == "peer" and symm_hdls is not None and f_ref is refs[i % n_sets]:
+            h = symm_hdls[i % n_sets]
+            h.barrier(channel=0)                                        # every rank's map for this step is in place
+            return h.get_buffer(int(src_of[rank]), (N, C, H, W), torch.float32)   # neighbour's HBM, read over NVLink by the staging kernel
         if args.exchange == "allgather":
             dist.all_gather_into_tensor(gathered_flat, f_ref)           # every map to every rank (BASELINE config 4 / MULTITEST)
             return gathered[src_of[rank]]
@@ -238,7 +253,7 @@ def run_ours(args, wl):
     def step(i):
         f_ref = refs[i % n_sets]
         if world > 1:
-            f_src = exchange(f_ref)
+            f_src = exchange(f_ref, i)
         else:
             f_src = srcs[i % n_sets]
         with torch.no_grad():
@@ -351,7 +366,7 @@ def run_ours(args, wl):
             "n_gpus": world, "steps": args.steps, "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "pairs_per_gpu": N, "C": C, "feat_hw": [H, W], "K": K,
-                       "parallelism": ("1 view per GPU, NCCL %s of per-view feature maps" % ("all-gather" if args.exchange == "allgather" else "send/recv (each rank receives only its source view)")) if world > 1 else "single GPU",
+                       "parallelism": ("1 view per GPU, NCCL %s of per-view feature maps" % ({"allgather": "all-gather", "p2p": "send/recv (each rank receives only its source view)", "peer": "symmetric memory: kernels read the source view from the neighbour GPU over NVLink, 1 barrier/step"}[args.exchange])) if world > 1 else "single GPU",
                        "l2": "rotating %d input sets (%.0f MB > 126 MB L2), no reuse between consecutive steps" % (n_sets, n_sets * set_bytes / 1e6),
                        "outputs": "finalout + attn + corr_pos", "variant": args.variant},
             "clocks": clocks,
@@ -380,7 +395,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default="auto", choices=["auto", "warp", "tile"])
-    ap.add_argument("--exchange", default="p2p", choices=["p2p", "allgather"], help="multi-GPU exchange of per-view feature maps")
+    ap.add_argument("--exchange", default="p2p", choices=["peer", "p2p", "allgather"], help="multi-GPU exchange of per-view feature maps")
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

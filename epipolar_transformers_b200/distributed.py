@@ -36,10 +36,12 @@ class ViewParallelFusion:
 
     def __init__(self, KRT_all, sampler: Optional[Callable] = None, group=None, fuse_fn: Optional[Callable] = None,
                  exchange: str = "p2p"):
-        """exchange='p2p': every rank receives only the map of its source view (send/recv permutation, (V-1)x
-        fewer bytes than an all-gather); exchange='allgather': every rank receives all maps (what BASELINE
-        config 4 names and what MULTITEST-style all-neighbour fusion needs)."""
-        if exchange not in ("p2p", "allgather"):
+        """exchange='peer': the per-view maps live in symmetric (peer-mapped) memory and the fused kernels read the
+        source view's map straight out of the neighbour GPU's HBM over NVLink — no copy, no collective, one
+        device-side barrier per step; exchange='p2p': NCCL send/recv permutation (each rank receives only its
+        source view's map); exchange='allgather': every rank receives all maps (what BASELINE config 4 names and
+        what MULTITEST-style all-neighbour fusion needs)."""
+        if exchange not in ("p2p", "allgather", "peer"):
             raise ValueError(exchange)
         self.exchange = exchange
         self.group = group
@@ -68,6 +70,30 @@ class ViewParallelFusion:
         dist.all_gather_into_tensor(self._buf, feat_view.contiguous(), group=self.group)
         return self._buf.view((self.world,) + tuple(feat_view.shape))
 
+    # ---- exchange='peer': symmetric memory -------------------------------------------------------------------
+    def alloc_view_buffers(self, shape, dtype=torch.float32, device=None, count: int = 2):
+        """`count` peer-mapped buffers for this rank's feature map (the backbone should write its output here).
+        Two buffers used alternately need only one barrier per step (see `peer_source`)."""
+        import torch.distributed._symmetric_memory as symm
+        device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+        group = self.group if self.group is not None else dist.group.WORLD
+        self._symm_bufs, self._symm_hdls = [], []
+        for _ in range(count):
+            t = symm.empty(*shape, dtype=dtype, device=device)
+            self._symm_hdls.append(symm.rendezvous(t, group))
+            self._symm_bufs.append(t)
+        self._symm_shape, self._symm_dtype, self._symm_i = tuple(shape), dtype, 0
+        return self._symm_bufs
+
+    def peer_source(self, slot: int) -> torch.Tensor:
+        """Barrier (all ranks have finished writing buffer `slot`), then a tensor aliasing the SOURCE rank's buffer
+        `slot` in that GPU's memory.  Reads of it travel over NVLink inside whatever kernel consumes it."""
+        h = self._symm_hdls[slot]
+        h.barrier(channel=0)
+        if self.world == 1:
+            return self._symm_bufs[slot]
+        return h.get_buffer(self.src, self._symm_shape, self._symm_dtype)
+
     def fetch_source(self, feat_view: torch.Tensor) -> torch.Tensor:
         """Point-to-point exchange: receive the source view's map, send ours to the ranks that fuse against it."""
         if self.world == 1:
@@ -83,7 +109,18 @@ class ViewParallelFusion:
 
     def __call__(self, feat_view: torch.Tensor):
         B = feat_view.shape[0]
-        feat_src = self.fetch_source(feat_view) if self.exchange == "p2p" else self.gather(feat_view)[self.src]
+        if self.exchange == "peer":
+            if getattr(self, "_symm_bufs", None) is None or self._symm_shape != tuple(feat_view.shape):
+                self.alloc_view_buffers(feat_view.shape, feat_view.dtype, feat_view.device)
+            slot = self._symm_i % len(self._symm_bufs)
+            self._symm_i += 1
+            if feat_view.data_ptr() != self._symm_bufs[slot].data_ptr():
+                self._symm_bufs[slot].copy_(feat_view)          # backbone did not write in place: one local copy
+            feat_src = self.peer_source(slot)
+        elif self.exchange == "p2p":
+            feat_src = self.fetch_source(feat_view)
+        else:
+            feat_src = self.gather(feat_view)[self.src]
         dev = feat_view.device
         P_ref = self.KRT_all[self.rank].to(dev).unsqueeze(0).expand(B, 3, 4).contiguous()
         P_src = self.KRT_all[self.src].to(dev).unsqueeze(0).expand(B, 3, 4).contiguous()
