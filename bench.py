@@ -220,13 +220,23 @@ def run_ours(args, wl):
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     symm_hdls = None
     if world > 1 and args.exchange == "peer":
-        import torch.distributed._symmetric_memory as symm
-        refs, symm_hdls = [], []
-        for _ in range(n_sets):                       # the "backbone output" buffers live in peer-mapped memory
-            t = symm.empty(N, C, H, W, dtype=torch.float32, device=dev)
-            symm_hdls.append(symm.rendezvous(t, dist.group.WORLD))
-            t.copy_(torch.relu(torch.randn(N, C, H, W, device=dev, generator=gen)))
-            refs.append(t)
+        try:
+            import torch.distributed._symmetric_memory as symm
+            refs, symm_hdls = [], []
+            for _ in range(n_sets):                       # the "backbone output" buffers live in peer-mapped memory
+                t = symm.empty(N, C, H, W, dtype=torch.float32, device=dev)
+                symm_hdls.append(symm.rendezvous(t, dist.group.WORLD))
+                t.copy_(torch.relu(torch.randn(N, C, H, W, device=dev, generator=gen)))
+                refs.append(t)
+            ok = torch.tensor([1], device=dev)
+        except Exception as e:                            # no peer mapping on this box: fall back to the collective
+            ok = torch.tensor([0], device=dev)
+            sys.stderr.write("bench.py: symmetric memory unavailable (%r), using all-gather\n" % (e,))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if int(ok.item()) == 0:
+            args.exchange = "allgather"
+            symm_hdls = None
+            refs = [torch.relu(torch.randn(N, C, H, W, device=dev, generator=gen)) for _ in range(n_sets)]
     else:
         refs = [torch.relu(torch.randn(N, C, H, W, device=dev, generator=gen)) for _ in range(n_sets)]
     srcs = [torch.relu(torch.randn(N, C, H, W, device=dev, generator=gen)) for _ in range(n_sets)]
@@ -395,7 +405,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
     ap.add_argument("--variant", default="auto", choices=["auto", "warp", "tile"])
-    ap.add_argument("--exchange", default="p2p", choices=["peer", "p2p", "allgather"], help="multi-GPU exchange of per-view feature maps")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "p2p", "allgather"], help="multi-GPU exchange of per-view feature maps")
     ap.add_argument("--cpu-steps", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
