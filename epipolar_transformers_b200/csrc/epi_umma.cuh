@@ -50,6 +50,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 // generic-proxy shared-memory writes -> visible to the async proxy (tcgen05.mma / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- 16-byte asynchronous copies global -> shared (LDGSTS), zero-fill when !valid ---------------------------
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src, bool valid) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(valid ? 16 : 0) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most n (0..3) of this thread's committed groups are still pending
+__device__ __forceinline__ void cp_async_wait_pending(int n) {
+    if (n <= 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    else if (n == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else if (n == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else asm volatile("cp.async.wait_group 3;" ::: "memory");
+}
+
 // ---- 1-D bulk copy global -> shared (TMA engine, UBLKCP), completion on an mbarrier ----------
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),

@@ -1,8 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-NG=$(nvidia-smi -L | wc -l)
-for EX in peer allgather; do
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $NG --steps 100 --warmup 10 --exchange $EX > gpurun_out/bench_n${NG}_${EX}.json 2> gpurun_out/bench_n${NG}_${EX}.err
-python -c "
-import json;d=json.loads(open('gpurun_out/bench_n${NG}_${EX}.json').read().strip().splitlines()[-1]);print('$EX', d['n_gpus'], round(d['value']), d['ms_per_step'], round(d['e2e']['value']), d['config']['parallelism'][:60])" || (head -c 300 gpurun_out/bench_n${NG}_${EX}.json; grep -E "Error|error" -B2 -A8 gpurun_out/bench_n${NG}_${EX}.err | head -40)
-done
+timeout 120 python tools/gpu_check.py tiny_ring_z cfg1_ring cfg2_r50_256_randn cfg3_r152_384 > gpurun_out/check.log 2>&1; echo "rc=$?" >> gpurun_out/check.log
+timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 300 python tools/gpu_timers.py 64 > gpurun_out/timers.log 2>&1
+timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_tile.json 2> gpurun_out/bench_tile.err
+timeout 120 python tools/gpu_mma_bench.py > gpurun_out/mma_bench.log 2>&1
+cat gpurun_out/check.log; tail -n 4 gpurun_out/pytest_gpu.log; head -12 gpurun_out/timers.log; python -c "import json;d=json.load(open('gpurun_out/bench_tile.json'));print(d['ms_per_step'], d['roofline']['kernel_ms'], d['e2e']['ms_per_step'])"; tail -n 3 gpurun_out/bench_tile.err; cat gpurun_out/mma_bench.log

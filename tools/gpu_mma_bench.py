@@ -5,11 +5,11 @@ import torch
 from epipolar_transformers_b200 import _lib
 lib = _lib.load()
 out = torch.zeros(4, dtype=torch.int64, device="cuda")
-for mn in (0, 1):
-    for N in (16, 32, 64, 128, 256):
-        for reps in (64, 256):
-            lib.epi_umma_bench(N, reps, mn, ctypes.c_void_p(out.data_ptr()), None)
+for M, mn in ((128, 0), (128, 1), (64, 0), (64, 1)):
+    for N in (32, 64, 128, 256):
+        for reps in (256,):
+            lib.epi_umma_bench(M, N, reps, mn, ctypes.c_void_p(out.data_ptr()), None)
             torch.cuda.synchronize()
             tot, issue = out[0].item(), out[1].item()
-            print("A %s N=%3d reps=%3d: total %7d cyc (%.1f / mma), issue loop %6d cyc (%.1f / mma)" %
-                  ("MN" if mn else "K ", N, reps, tot, tot / reps, issue, issue / reps))
+            print("M=%3d A %s N=%3d reps=%3d: total %7d cyc (%.1f / mma), issue loop %6d cyc (%.1f / mma)" %
+                  (M, "MN" if mn else "K ", N, reps, tot, tot / reps, issue, issue / reps))
