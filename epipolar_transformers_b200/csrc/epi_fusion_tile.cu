@@ -69,6 +69,10 @@ struct Misc {
 };
 static_assert(sizeof(Misc) <= 256, "Misc too large");
 
+// CTA-wide rendezvous for the warp-specialised sections: worker warps and the MMA warp run different loops, so the
+// barrier lives in ONE non-inlined function — every thread of the CTA arrives at the same bar.sync instruction.
+__device__ __noinline__ void cta_sync_named() { __syncthreads(); }
+
 __device__ __forceinline__ void bounded_wait(uint64_t *bar, uint32_t parity) {
     for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
         if (it > (1u << 26)) __trap();      // a protocol bug must abort the launch, never hang the GPU
@@ -327,13 +331,13 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_tile_kernel(const Fusion
                 if (st + 1 < n_st) gather_load(v, (st + 1) / NH, (st + 1) % NH);
                 fence_proxy_async_smem();
                 tc_fence_before();
-                __syncthreads();
+                cta_sync_named();
                 n_stage++;
             }
         } else {
             for (int st = 0; st < n_st; st++) {
                 const int c = st / NH, h = st % NH;
-                __syncthreads();                                   // stage st is in shared memory
+                cta_sync_named();                                   // stage st is in shared memory
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t idesc64 = make_idesc_bf16(128, 2 * TM, 0, 0), idesc32 = make_idesc_bf16(128, TM, 0, 0);
@@ -526,13 +530,13 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_tile_kernel(const Fusion
                 }
                 fence_proxy_async_smem();
                 tc_fence_before();
-                __syncthreads();
+                cta_sync_named();
                 n_stage++;
             }
         } else {
             for (int st = 0; st < n_st; st++) {
                 const int c = st / NH, h = st % NH;
-                __syncthreads();
+                cta_sync_named();
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t idesc64 = make_idesc_bf16(128, 2 * TM, 1, 0), idesc32 = make_idesc_bf16(128, TM, 1, 0);
