@@ -7,9 +7,13 @@
 // One CTA per 128 pixels: D[128 px, C out] = X[128 px, C]·Wfᵀ with X supplied by the fusion kernel as bf16
 // (hi, lo) planes [N·HW, C] (K-major rows) and Wf split to (hi, lo) while it is staged.  Three MMAs per
 // product (hi·hi + hi·lo + lo·hi), fp32 accumulation in TMEM (M=128, N=C<=256), K streamed in 64-channel
-// panels through a double-buffered shared-memory ring; the epilogue adds bias/residuals and writes NCHW
+// panels through a double-buffered shared-memory ring — the X panels arrive by TMA (cp.async.bulk.tensor.2d with the
+// 128-byte swizzle the UMMA descriptors expect, completion on an mbarrier); the epilogue adds bias/residuals and writes NCHW
 // (a warp's lanes are 32 consecutive pixels, so every store instruction is one 128-byte line per channel).
+#include <cuda.h>
 #include <cuda_bf16.h>
+
+#include <cstring>
 
 #include "epi_kernels.cuh"
 #include "epi_umma.cuh"
@@ -23,13 +27,22 @@ constexpr uint32_t A_PLANE = 16384;                 // 128 rows x 128 B
 constexpr uint32_t B_PLANE = 32768;                 // 256 rows x 128 B
 constexpr uint32_t STAGE = 2 * A_PLANE + 2 * B_PLANE;   // 96 KB
 constexpr uint32_t SMEM_ALLOC = 2 * STAGE + 1024 + 64;
+
+// 2-D tiled TMA load of a [128 rows x 64 bf16] box into a swizzled panel, completion counted on `bar`
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     umma::smem_u32(smem_dst)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(umma::smem_u32(bar))
+                 : "memory");
+}
 }  // namespace zg
 
-__global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z) {
+__global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z, const __grid_constant__ CUtensorMap tm_hi,
+                                                              const __grid_constant__ CUtensorMap tm_lo, const int use_tma) {
     using namespace zg;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * STAGE);       // [0,1] stage, [2] all
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * STAGE);       // [0,1] MMAs done with stage, [2] all, [3] TMA landed
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * STAGE + 32);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = z.C, HW = z.HW, W = z.W;
@@ -39,7 +52,11 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z)
     const __nv_bfloat16 *xh = z.x_hi + (size_t)n * HW * C, *xl = z.x_lo + (size_t)n * HW * C;
 
     if (warp == 0) tmem_alloc(tmem_slot, 256);
-    if (tid == 32) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
+    if (tid == 32) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1); mbar_fence_init(); }
+    if (tid == 0 && use_tma) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -49,8 +66,14 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z)
         const uint32_t buf = q & 1;
         uint8_t *st = smem + buf * STAGE;
         if (q >= 2) { for (uint32_t it = 0; !mbar_try_wait(&bars[buf], ((q >> 1) + 1) & 1); ++it) if (it > (1u << 26)) __trap(); }
-        // A: 128 pixel rows x 64 channels of both planes (16-byte chunks, 8 lanes per row)
-        {
+        // A: 128 pixel rows x 64 channels of both planes
+        if (use_tma) {
+            if (tid == 0) {                                     // one thread arms the barrier and issues both boxes
+                mbar_arrive_expect_tx(&bars[3], 2 * A_PLANE);
+                tma_load_2d(st, &tm_hi, q * 64, n * HW + p0, &bars[3]);
+                tma_load_2d(st + A_PLANE, &tm_lo, q * 64, n * HW + p0, &bars[3]);
+            }
+        } else {                                                // 16-byte chunks, 8 lanes per row
             const int j = tid & 7;
 #pragma unroll
             for (int it = 0; it < 8; it++) {
@@ -93,6 +116,7 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z)
         __syncthreads();
         tc_fence_after();
         if (tid == 0) {
+            if (use_tma) { for (uint32_t it = 0; !mbar_try_wait(&bars[3], q & 1); ++it) if (it > (1u << 26)) __trap(); }
             const uint32_t idesc = make_idesc_bf16(128, z.Npad, 0, 0);
             const uint32_t sa = smem_u32(st), sb = sa + 2 * A_PLANE;
 #pragma unroll
@@ -154,11 +178,42 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z)
 
 bool zgemm_supported(int C) { return C % 16 == 0 && C >= 16 && C <= 256; }
 
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) p = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+// [rows = N*HW, cols = C] bf16 plane, box = 64 columns x 128 rows, 128-byte swizzle (what the UMMA K-major descriptor reads)
+bool make_plane_map(CUtensorMap *m, const __nv_bfloat16 *base, int rows, int C) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn || C % 8 != 0) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+    const cuuint32_t box[2] = {64u, 128u};
+    const cuuint32_t estr[2] = {1u, 1u};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16 *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
 cudaError_t launch_zgemm(const ZGemmArgs &z, cudaStream_t st) {
     const int tiles = (z.HW + 127) / 128;
     cudaError_t e = cudaFuncSetAttribute(epi_zgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zg::SMEM_ALLOC);
     if (e != cudaSuccess) return e;
-    epi_zgemm_kernel<<<z.N * tiles, zg::NT, zg::SMEM_ALLOC, st>>>(z);
+    CUtensorMap tm_hi, tm_lo;
+    memset(&tm_hi, 0, sizeof(tm_hi)); memset(&tm_lo, 0, sizeof(tm_lo));
+    // TMA needs whole 64-column boxes inside the row pitch; otherwise the LDG path stages A
+    const int use_tma = (z.C % 64 == 0) && make_plane_map(&tm_hi, z.x_hi, z.N * z.HW, z.C) && make_plane_map(&tm_lo, z.x_lo, z.N * z.HW, z.C);
+    epi_zgemm_kernel<<<z.N * tiles, zg::NT, zg::SMEM_ALLOC, st>>>(z, tm_hi, tm_lo, use_tma);
     return cudaGetLastError();
 }
 
