@@ -188,7 +188,7 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("EPI_NCCL_DEBUG", "WARN")       # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")                   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -203,15 +203,22 @@ def run_ours(args, wl):
 
     # cameras: `max(world,4)` views on a ring; single-GPU: pair v = (view v, nearest view), like the
     # H36M test-time batch.  Multi-GPU: rank r owns view r, N frames of it.
-    V = max(world, 4) if world > 1 else N
-    KRT = syn.ring_cameras(V, 4 * H)[:max(world, 1) if world > 1 else N]      # cameras that exist = the ranks
-    src_of = syn.nearest_source(KRT)
+    # The same 4-camera H36M-like ring at every N, so per-GPU work does not change with N (weak scaling): at N=1
+    # the 4 pairs are (cam v, nearest cam) for v=0..3; at N>1 rank r owns camera r%4 (N frames of it) and fuses
+    # against the rank that owns its nearest camera inside the same group of 4 ranks.
+    ring = syn.ring_cameras(4, 4 * H)
+    ring_src = syn.nearest_source(ring)
     if world == 1:
-        P_ref = torch.from_numpy(KRT.astype(np.float32)).to(dev)
-        P_src = torch.from_numpy(KRT[src_of].astype(np.float32)).to(dev)
+        src_of = ring_src
+        P_ref = torch.from_numpy(ring.astype(np.float32)).to(dev)
+        P_src = torch.from_numpy(ring[ring_src].astype(np.float32)).to(dev)
     else:
-        P_ref = torch.from_numpy(np.repeat(KRT[rank:rank + 1], N, 0).astype(np.float32)).to(dev)
-        P_src = torch.from_numpy(np.repeat(KRT[src_of[rank]:src_of[rank] + 1], N, 0).astype(np.float32)).to(dev)
+        cam = np.arange(world) % 4
+        src_of = (np.arange(world) // 4) * 4 + ring_src[cam]
+        src_of = np.where(src_of < world, src_of, (np.arange(world) // 4) * 4 + (cam ^ 1))      # world not a multiple of 4
+        src_of = np.where(src_of < world, src_of, (np.arange(world) + 1) % world)
+        P_ref = torch.from_numpy(np.repeat(ring[cam[rank]][None], N, 0).astype(np.float32)).to(dev)
+        P_src = torch.from_numpy(np.repeat(ring[cam[src_of[rank]]][None], N, 0).astype(np.float32)).to(dev)
 
     # rotating input sets so consecutive steps never find their inputs in L2
     set_bytes = 2 * N * C * H * W * 4
