@@ -174,6 +174,11 @@ def run_reference_arm(args, wl):
 # our arm
 # ----------------------------------------------------------------------------------------------
 def run_ours(args, wl):
+    # stdout must carry exactly one JSON line: native libraries (NCCL prints its version with printf when
+    # NCCL_DEBUG=VERSION is set on the box) write to fd 1, so fd 1 points at stderr until the line is printed.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     import epipolar_transformers_b200 as epi
@@ -188,7 +193,7 @@ def run_ours(args, wl):
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")                   # keep stdout to the one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -399,7 +404,10 @@ def run_ours(args, wl):
             r = time_cpu_port(wl, args.cpu_steps, 1)
             line["cpu_baseline"] = {"value": r["views_per_s"], "unit": "views/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"], "ms_per_step": r["ms_per_step"]}
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 

@@ -1,9 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-NG=$(nvidia-smi -L | wc -l)
-timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29541 bench.py --gpus $NG --steps 100 --warmup 10 > gpurun_out/bench_n${NG}_peer.json 2> gpurun_out/bench_n${NG}_peer.err
-python -c "
-import json;d=json.loads(open('gpurun_out/bench_n${NG}_peer.json').read().strip().splitlines()[-1]);print('default', d['n_gpus'], round(d['value']), d['ms_per_step'], round(d['e2e']['value']), d['config']['parallelism'][:70])" || (head -c 300 gpurun_out/bench_n${NG}_peer.json; grep -E "Error|error" -B2 -A8 gpurun_out/bench_n${NG}_peer.err | head -40)
-wc -l gpurun_out/bench_n${NG}_peer.json
-timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29542 bench.py --impl reference --gpus $NG --steps 3 --warmup 1 > gpurun_out/bench_n${NG}_ref.json 2> gpurun_out/bench_n${NG}_ref.err
-cut -c1-200 gpurun_out/bench_n${NG}_ref.json
+timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 400 python bench.py > gpurun_out/bench_final_n1.json 2> gpurun_out/bench_final_n1.err
+timeout 300 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_final_ref.json 2> gpurun_out/bench_final_ref.err
+timeout 300 python bench.py --workload cfg3 --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_final_cfg3.json 2> gpurun_out/bench_final_cfg3.err
+./tools/profile_round.sh r1 > gpurun_out/profile_round.log 2>&1
+tail -n 3 gpurun_out/smoke.log; tail -n 3 gpurun_out/pytest_gpu.log; wc -l gpurun_out/bench_final_n1.json; cat gpurun_out/bench_final_n1.json | cut -c1-3000; cut -c1-400 gpurun_out/bench_final_ref.json; python -c "import json;d=json.load(open('gpurun_out/bench_final_cfg3.json'));print('cfg3', d['ms_per_step'], d['roofline']['kernel_ms'], d['roofline']['frac'])"
