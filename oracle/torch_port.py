@@ -20,7 +20,9 @@ from . import epipolar_oracle as eo
 
 
 def forward(cfg, feat_ref, feat_src, P_ref, P_src, params=None, locs=None, threads=None):
-    """feat_*: torch CPU float32 [N,C,H,W]; P_*: numpy/torch [N,3,4].  Returns (finalout, corr_pos, attn)."""
+    """feat_*: torch float32 [N,C,H,W] (CPU for the baseline; a CUDA tensor runs the same ATen op sequence on the
+    GPU, which is the "reference PyTorch forward on the same B200" of BASELINE.md B2); P_*: numpy [N,3,4].
+    Returns (finalout, corr_pos, attn)."""
     if threads:
         torch.set_num_threads(int(threads))
     N, C, H, W = feat_ref.shape
@@ -31,7 +33,7 @@ def forward(cfg, feat_ref, feat_src, P_ref, P_src, params=None, locs=None, threa
         if locs is None:
             locs = eo.sample_locs(cfg, np.asarray(P_ref, np.float32), np.asarray(P_src, np.float32), H, W, K,
                                   dtype=np.float32, geometry="reference")
-        grid = torch.as_tensor(np.asarray(locs), dtype=torch.float32)            # [K,N,H,W,2]
+        grid = torch.as_tensor(np.asarray(locs), dtype=torch.float32).to(feat_ref.device)   # [K,N,H,W,2]
         src_k = feat_src.unsqueeze(0).expand(K, N, C, H, W)                      # stride-0 view over K
         fused, corr, weights = [], [], []
         for n in range(N):
@@ -43,12 +45,13 @@ def forward(cfg, feat_ref, feat_src, P_ref, P_src, params=None, locs=None, threa
             sim = F.softmax(sim * scale, 0)
             top = sim.argmax(0)
             pos = torch.gather(g, 0, top.view(1, H, W, 1).expand(-1, -1, -1, 2)).squeeze(0)
-            corr.append(torch.as_tensor(eo.de_normalize(pos.numpy(), H, W, correct)))
+            wh = torch.tensor([W, H], dtype=pos.dtype, device=pos.device)
+            corr.append((pos + 1) * (wh - 1) / 2.0 if correct else (pos + 1) * wh / 2.0 - 0.5)      # de_normalize, multiview.py:39-57
             fused.append((vals * sim.view(K, 1, H, W)).sum(0))
             weights.append(sim)
         out = torch.stack(fused)
         if "z" in cfg.EPIPOLAR.PARAMETERIZED:
-            p = {k: torch.as_tensor(v) for k, v in params.items()}
+            p = {k: torch.as_tensor(v).to(out.device) for k, v in params.items()}
             y = F.conv2d(out, p["z.weight"], p["z.bias"])
             y = F.batch_norm(y, p["bn.running_mean"], p["bn.running_var"], p["bn.weight"], p["bn.bias"], False, 0.1, 1e-5)
             out = y + out if cfg.EPIPOLAR.ZRESIDUAL else y
