@@ -26,12 +26,13 @@ bool src_is_channels_last(const EpiFusionParams *p) {
 }
 
 struct Plan {
-    size_t off_src = 0, off_prez = 0, off_counter = 0, total = 0;
-    bool stage_src = false, has_z = false, tile = false;
+    size_t off_src = 0, off_prez = 0, off_counter = 0, off_ref = 0, off_order = 0, total = 0;
+    bool stage_src = false, has_z = false, tile = false, sector = false;
 };
 
 bool want_tile(const EpiFusionParams *p) {
     if (p->variant == EPI_VARIANT_WARP) return false;
+    if (p->variant == EPI_VARIANT_SECTOR && p->sample_locs_in != nullptr) return false;
     return epi::fusion_tile_shape_ok(p->C, p->H, p->W, p->K, p->sample_locs_in != nullptr);
 }
 
@@ -39,12 +40,19 @@ Plan make_plan(const EpiFusionParams *p) {
     Plan pl;
     const size_t map = (size_t)p->N * p->C * p->H * p->W * sizeof(float);
     pl.tile = want_tile(p);
+    // sector tiles (pixels grouped by epipolar angle) need the fused geometry; injected locations and an explicit
+    // EPI_VARIANT_TILE request use the 4x8 block tiles
+    pl.sector = pl.tile && p->variant != EPI_VARIANT_TILE && p->sample_locs_in == nullptr;
     pl.stage_src = pl.tile || !src_is_channels_last(p);      // tile kernel: bf16 (hi, lo) planes, same bytes as one fp32 map
     pl.has_z = p->z_weight_folded != nullptr;
     size_t off = 0;
     if (pl.stage_src) { pl.off_src = off; off += align_up(map); }
     if (pl.has_z) { pl.off_prez = off; off += align_up(map); }
     if (pl.tile) { pl.off_counter = off; off += 256; }
+    if (pl.sector) {
+        pl.off_ref = off; off += align_up(map);
+        pl.off_order = off; off += align_up((size_t)p->N * p->H * p->W * sizeof(uint16_t));
+    }
     pl.total = off;
     return pl;
 }
@@ -58,7 +66,7 @@ int validate(const EpiFusionParams *p) {
     if (p->C > 1024 || (p->C > 512 && p->C % 4 != 0)) return fail(EPI_EINVAL, "C must be <= 512, or <= 1024 and a multiple of 4");
     if (!(p->downsample > 0.f) || !(p->img_scale > 0.f)) return fail(EPI_EINVAL, "downsample and img_scale must be positive");
     if (p->z_weight_folded && !p->z_bias_folded) return fail(EPI_EINVAL, "z_bias_folded required with z_weight_folded");
-    if (p->variant < EPI_VARIANT_AUTO || p->variant > EPI_VARIANT_TILE) return fail(EPI_EINVAL, "unknown variant");
+    if (p->variant < EPI_VARIANT_AUTO || p->variant > EPI_VARIANT_SECTOR) return fail(EPI_EINVAL, "unknown variant");
     return EPI_OK;
 }
 
@@ -112,6 +120,7 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
     a.geom = make_geom(p->H, p->W, p->K, p->downsample, p->img_scale, p->eps, p->correct_normalize, p->align_corners);
 
     if (p->variant == EPI_VARIANT_TILE && !pl.tile) return fail(EPI_EINVAL, "tile variant does not support this shape");
+    if (p->variant == EPI_VARIANT_SECTOR && !pl.sector) return fail(EPI_EINVAL, "sector variant does not support this shape / injected locations");
     if (pl.tile) {
         __nv_bfloat16 *hi = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_src);
         __nv_bfloat16 *lo = hi + (size_t)p->N * p->C * p->H * p->W;
@@ -120,6 +129,17 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
         if (e != cudaSuccess) return fail(EPI_ECUDA, "operand staging launch failed: %s", cudaGetErrorString(e));
         launches++;
         a.src_hi = hi; a.src_lo = lo;
+        if (pl.sector) {
+            __nv_bfloat16 *rhi = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_ref);
+            __nv_bfloat16 *rlo = rhi + (size_t)p->N * p->C * p->H * p->W;
+            e = epi::launch_split_planes(p->feat_ref, p->ref_stride, rhi, rlo, p->N, p->C, p->H, p->W, nullptr, st);
+            if (e != cudaSuccess) return fail(EPI_ECUDA, "reference staging launch failed: %s", cudaGetErrorString(e));
+            uint16_t *order = reinterpret_cast<uint16_t *>(ws + pl.off_order);
+            e = epi::launch_sector_order(p->P_ref, p->P_src, order, p->N, a.geom, st);
+            if (e != cudaSuccess) return fail(EPI_ECUDA, "sector ordering launch failed: %s", cudaGetErrorString(e));
+            launches += 2;
+            a.ref_hi = rhi; a.ref_lo = rlo; a.order = order;
+        }
     } else if (pl.stage_src) {
         float *nhwc = reinterpret_cast<float *>(ws + pl.off_src);
         e = epi::launch_nchw_to_nhwc(p->feat_src, p->src_stride, nhwc, p->N, p->C, p->H, p->W, st);

@@ -11,6 +11,8 @@ struct FusionArgs {
     const float *feat_ref;  int64_t ref_stride[4];
     const float *src_nhwc;                    // [N,H,W,C] contiguous, 16-byte aligned (zero-copy or staged) — warp kernel
     const __nv_bfloat16 *src_hi, *src_lo;     // [N,H,W,C] bf16 planes, src ≈ hi + lo — tile kernel
+    const __nv_bfloat16 *ref_hi, *ref_lo;     // same for feat_ref — sector tiles only
+    const uint16_t *order;                    // [N,H*W] pixels sorted by epipolar angle — sector tiles only (else null)
     const float *P_ref, *P_src;
     const float *locs_in;
     float *out;             int64_t out_stride[4];
@@ -49,6 +51,7 @@ cudaError_t launch_fusion_warp(const FusionArgs &a, cudaStream_t st);
 cudaError_t launch_fusion_tile(const FusionArgs &a, cudaStream_t st);
 bool fusion_tile_supported(const FusionArgs &a);
 bool fusion_tile_shape_ok(int C, int H, int W, int K, bool has_locs_in);
+cudaError_t launch_sector_order(const float *P_ref, const float *P_src, uint16_t *order, int N, const GeomCfg &gc, cudaStream_t st);
 cudaError_t launch_split_planes(const float *src, const int64_t stride[4], __nv_bfloat16 *hi, __nv_bfloat16 *lo, int N, int C,
                                 int H, int W, int *zero_me, cudaStream_t st);
 

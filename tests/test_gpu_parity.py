@@ -109,10 +109,13 @@ def test_T2_geometry_vs_fp64(name):
         assert err < 1e-3 and err <= max(ref_err, 1e-4), (err, ref_err)
 
 
-@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("variant", ["warp", "auto", "tile"])
 @pytest.mark.parametrize("name", FULL + BIG)
 def test_T3_end_to_end_vs_oracle(name, variant):
-    """Own geometry end to end: the locations the kernel sampled are fed to the C oracle."""
+    """Own geometry end to end: the locations the kernel sampled are fed to the C oracle.
+    ('auto' = epipolar-sector tiles where the shape allows, 'tile' = 4x8 block tiles, 'warp' = CUDA-core kernel.)"""
+    if variant == "tile" and gc.CASES[name]["C"] % 8 != 0:
+        pytest.skip("tensor-core kernel needs C % 8 == 0")
     (cfg, f1, f2, P1, P2, params), r = run_kernel(name, variant=variant)
     o = c_oracle.forward(cfg, f1, f2, P1, P2, locs=r["sample_locs"])
     out = eo.z_epilogue(o["out"], params, cfg.EPIPOLAR.ZRESIDUAL) if params else o["out"]

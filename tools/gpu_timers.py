@@ -8,19 +8,21 @@ import epipolar_transformers_b200 as epi
 from epipolar_transformers_b200 import synthetic as syn
 lib = _lib.load()
 N, C, H, W, K = 4, 256, int(sys.argv[1]) if len(sys.argv) > 1 else 64, 0, 64
+VARIANT = sys.argv[2] if len(sys.argv) > 2 else "auto"
 W = H
 P1, P2 = syn.pairs_from_ring(N, 4 * H)
 f1 = torch.relu(torch.randn(N, C, H, W, device="cuda")); f2 = torch.relu(torch.randn(N, C, H, W, device="cuda"))
 P1 = torch.from_numpy(P1.astype(np.float32)).cuda(); P2 = torch.from_numpy(P2.astype(np.float32)).cuda()
 buf = (ctypes.c_ulonglong * 16)()
 for it in range(3):
-    epi.epipolar_fusion(f1, f2, P1, P2, K=K, correct_normalize=True)
+    epi.epipolar_fusion(f1, f2, P1, P2, K=K, correct_normalize=True, variant=VARIANT)
     torch.cuda.synchronize()
     lib.epi_tile_timers_read(buf, 1)
 v = np.array(list(buf), dtype=np.float64)
 names = ["mark+prefix", "idx+Qstage", "phaseA(gather+mma)", "B1", "B2", "attnflush", "phaseC", "phaseD"]
 groups = v[8]
 tiles = N * ((H + 3) // 4) * ((W + 7) // 8)
+print("variant", VARIANT)
 print("groups %d tiles %d (%.2f groups/tile)" % (groups, tiles, groups / tiles))
 tot = v[:8].sum()
 for nm, x in zip(names, v[:8]):
