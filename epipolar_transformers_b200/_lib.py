@@ -16,7 +16,8 @@ EPI_VARIANT_AUTO, EPI_VARIANT_WARP, EPI_VARIANT_TILE, EPI_VARIANT_SECTOR = 0, 1,
 VARIANTS = {"auto": EPI_VARIANT_AUTO, "warp": EPI_VARIANT_WARP, "tile": EPI_VARIANT_TILE, "sector": EPI_VARIANT_SECTOR}
 
 EXPORTS = ("epi_version", "epi_last_error", "epi_fusion_workspace_bytes", "epi_fusion_forward_f32",
-           "epi_sample_locs_f32", "epi_fold_z_bn_f32", "epi_last_launch_count", "epi_umma_selftest")
+           "epi_sample_locs_f32", "epi_fold_z_bn_f32", "epi_last_launch_count", "epi_umma_selftest",
+           "epi_kernel_timing_enable", "epi_kernel_timing_last_ms")
 
 _fp = ctypes.POINTER(ctypes.c_float)
 
@@ -71,6 +72,9 @@ def load():
     lib.epi_umma_selftest.restype = ctypes.c_int
     lib.epi_umma_selftest.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
                                       ctypes.c_int, ctypes.c_void_p]
+    lib.epi_kernel_timing_enable.restype = ctypes.c_int
+    lib.epi_kernel_timing_enable.argtypes = [ctypes.c_int]
+    lib.epi_kernel_timing_last_ms.restype = ctypes.c_float
     v = lib.epi_version()
     if v != EPI_ABI_VERSION:
         raise RuntimeError("libepipolar_b200.so ABI version %d != expected %d" % (v, EPI_ABI_VERSION))

@@ -10,6 +10,8 @@ namespace {
 
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
+thread_local int g_timing = 0, g_timing_valid = 0;
+thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 
 int fail(int code, const char *fmt, const char *detail = "") {
     snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -94,6 +96,15 @@ const char *epi_last_error(void) { return g_err; }
 
 int epi_last_launch_count(void) { return g_launches; }
 
+int epi_kernel_timing_enable(int on) { g_timing = on ? 1 : 0; return EPI_OK; }
+
+float epi_kernel_timing_last_ms(void) {
+    if (!g_timing_valid || !g_ev0) return -1.f;
+    float ms = -1.f;
+    if (cudaEventSynchronize(g_ev1) != cudaSuccess || cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.f;
+    return ms;
+}
+
 size_t epi_fusion_workspace_bytes(const EpiFusionParams *p) {
     if (!p || p->N <= 0 || p->C <= 0 || p->H <= 0 || p->W <= 0) return 0;
     return make_plan(p).total;
@@ -169,8 +180,14 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
 
     const bool use_tile = pl.tile && epi::fusion_tile_supported(a);
     if (pl.tile && !use_tile) return fail(EPI_EINVAL, "internal: tile plan without tile support");
+    g_timing_valid = 0;
+    if (g_timing) {
+        if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
+        cudaEventRecord(g_ev0, st);
+    }
     e = use_tile ? epi::launch_fusion_tile(a, st) : epi::launch_fusion_warp(a, st);
     if (e != cudaSuccess) return fail(EPI_ECUDA, "fusion kernel launch failed: %s", cudaGetErrorString(e));
+    if (g_timing) { cudaEventRecord(g_ev1, st); g_timing_valid = 1; }
     launches++;
 
     if (z_tc) {

@@ -107,6 +107,12 @@ int epi_fold_z_bn_f32(const float *z_weight, const float *z_bias, const float *b
  * split=1: bf16 (hi,lo) three-term products).  All pointers device fp32, row-major. */
 int epi_umma_selftest(int mode, const float *A, const float *B, float *D, int N, int K, int split, void *stream);
 
+/* Measurement aid (bench.py roofline): when enabled on this thread, epi_fusion_forward_f32 brackets its dominant
+ * kernel (the fused attention kernel) with CUDA events on the caller's stream; epi_kernel_timing_last_ms()
+ * synchronises on them and returns that launch's duration in milliseconds (< 0 if there is none). */
+int epi_kernel_timing_enable(int on);
+float epi_kernel_timing_last_ms(void);
+
 /* Number of kernels the last successful epi_fusion_forward_f32 on this thread launched. */
 int epi_last_launch_count(void);
 

@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
-timeout 300 python __graft_entry__.py --smoke > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke.log
-timeout 400 python bench.py --cpu-steps 4 > gpurun_out/bench_final_n1.json 2> gpurun_out/bench_final_n1.err
-./tools/profile_round.sh r1 > gpurun_out/profile_round.log 2>&1
-tail -n 4 gpurun_out/pytest_gpu.log; tail -n 2 gpurun_out/smoke.log; cat gpurun_out/bench_final_n1.json | cut -c1-2600
+timeout 300 python -m pytest tests -m gpu -q -x -k "T3 or module or streamer or mpjpe or sweep" > gpurun_out/pytest_gpu.log 2>&1; echo "rc=$?" >> gpurun_out/pytest_gpu.log
+timeout 300 python bench.py --no-cpu-baseline > gpurun_out/bench_final_nocpu.json 2> gpurun_out/bench_final_nocpu.err
+timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"epi|split|nchw|z_epi|sector" -c 60 --csv --log-file gpurun_out/launches_r1.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/launches_r1.log 2>&1
+tail -n 3 gpurun_out/pytest_gpu.log; cat gpurun_out/bench_final_nocpu.json | cut -c1-2400; tail -n 3 gpurun_out/bench_final_nocpu.err

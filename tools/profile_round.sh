@@ -4,7 +4,7 @@
 TAG=${1:-r1}
 mkdir -p gpurun_out
 BENCH="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"epi|split|nchw|z_epi" -c 60 --csv \
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"epi|split|nchw|z_epi|sector" -c 60 --csv \
     --log-file gpurun_out/launches_${TAG}.csv $BENCH > gpurun_out/launches_${TAG}.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:epi_fusion_tile -s 2 -c 1 -f \
     -o gpurun_out/prof_tile_${TAG} $BENCH > gpurun_out/prof_tile_${TAG}.log 2>&1

@@ -17,15 +17,16 @@ rows = [r for r in csv.DictReader(l for l in open(lp) if not l.startswith("=="))
 agg = defaultdict(list)
 for r in rows:
     agg[r["Kernel Name"].split("(")[0]].append(float(r["Metric Value"]) / 1000.0)
-per_step = {k: sum(v) / len(v) for k, v in agg.items()}
+nsteps = max(1, max((len(v) for k, v in agg.items() if "fusion" in k), default=1))      # one fused-kernel launch per step
+per_step = {k: sum(v) / nsteps for k, v in agg.items()}                                  # time per step (a kernel may launch twice)
 tot = sum(per_step.values())
 with open(os.path.join(PR, "launches_%s.md" % TAG), "w") as f:
     f.write("# ncu launch list, `python bench.py --steps 3 --warmup 3` (cfg2), %s\n\n" % TAG)
     f.write("`ncu --metrics gpu__time_duration.sum --clock-control none` — cold-cache, serialised: compare shares.\n\n")
-    f.write("| kernel | launches | mean us | share of step |\n|---|---:|---:|---:|\n")
+    f.write("| kernel | launches | us per step | share of step |\n|---|---:|---:|---:|\n")
     for k, v in sorted(per_step.items(), key=lambda x: -x[1]):
         f.write("| `%s` | %d | %.1f | %.1f %% |\n" % (k, len(agg[k]), v, 100 * v / tot))
-    f.write("\nsum of means per step: %.1f us\n" % tot)
+    f.write("\nsum per step: %.1f us (%d steps captured)\n" % (tot, nsteps))
 os.replace(lp, os.path.join(PR, "launches_%s.csv" % TAG)) if False else None
 import shutil
 shutil.copy(lp, os.path.join(PR, "launches_%s.csv" % TAG))
