@@ -28,9 +28,14 @@ bool src_is_channels_last(const EpiFusionParams *p) {
 }
 
 struct Plan {
-    size_t off_src = 0, off_prez = 0, off_counter = 0, off_ref = 0, off_order = 0, total = 0;
-    bool stage_src = false, has_z = false, tile = false, sector = false;
+    size_t off_src = 0, off_prez = 0, off_counter = 0, off_ref = 0, off_order = 0, off_order_tmp = 0, off_geom = 0, total = 0;
+    bool stage_src = false, has_z = false, tile = false, sector = false, pipe = false;
 };
+
+bool want_pipe(const EpiFusionParams *p) {
+    if (p->variant != EPI_VARIANT_AUTO && p->variant != EPI_VARIANT_PIPE) return false;
+    return epi::fusion_pipe_shape_ok(p->C, p->H, p->W, p->K, p->sample_locs_in != nullptr);
+}
 
 bool want_tile(const EpiFusionParams *p) {
     if (p->variant == EPI_VARIANT_WARP) return false;
@@ -41,6 +46,20 @@ bool want_tile(const EpiFusionParams *p) {
 Plan make_plan(const EpiFusionParams *p) {
     Plan pl;
     const size_t map = (size_t)p->N * p->C * p->H * p->W * sizeof(float);
+    pl.pipe = want_pipe(p);
+    if (pl.pipe) {
+        // [ref_hi | ref_lo | src_hi | src_lo] bf16 planes (bytes of two fp32 maps), pre-z planes, pixel order, pair constants
+        pl.has_z = p->z_weight_folded != nullptr;
+        size_t off = 0;
+        pl.off_ref = off; off += align_up(2 * map);
+        if (pl.has_z) { pl.off_prez = off; off += align_up(map); }
+        pl.off_counter = off; off += 256;
+        pl.off_order = off; off += align_up((size_t)p->N * p->H * p->W * sizeof(uint16_t));
+        pl.off_order_tmp = off; off += align_up((size_t)p->N * p->H * p->W * sizeof(uint16_t));
+        pl.off_geom = off; off += align_up((size_t)p->N * sizeof(epi::PairGeom));
+        pl.total = off;
+        return pl;
+    }
     pl.tile = want_tile(p);
     // sector tiles (pixels grouped by epipolar angle) need the fused geometry; injected locations and an explicit
     // EPI_VARIANT_TILE request use the 4x8 block tiles
@@ -68,7 +87,9 @@ int validate(const EpiFusionParams *p) {
     if (p->C > 1024 || (p->C > 512 && p->C % 4 != 0)) return fail(EPI_EINVAL, "C must be <= 512, or <= 1024 and a multiple of 4");
     if (!(p->downsample > 0.f) || !(p->img_scale > 0.f)) return fail(EPI_EINVAL, "downsample and img_scale must be positive");
     if (p->z_weight_folded && !p->z_bias_folded) return fail(EPI_EINVAL, "z_bias_folded required with z_weight_folded");
-    if (p->variant < EPI_VARIANT_AUTO || p->variant > EPI_VARIANT_SECTOR) return fail(EPI_EINVAL, "unknown variant");
+    if (p->variant < EPI_VARIANT_AUTO || p->variant > EPI_VARIANT_PIPE) return fail(EPI_EINVAL, "unknown variant");
+    if (p->z_weight_folded && (reinterpret_cast<uintptr_t>(p->z_weight_folded) % 16 != 0 || reinterpret_cast<uintptr_t>(p->z_bias_folded) % 4 != 0))
+        return fail(EPI_EINVAL, "z_weight_folded must be 16-byte aligned (contiguous [C,C]) and z_bias_folded 4-byte aligned");
     return EPI_OK;
 }
 
@@ -130,6 +151,21 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
     for (int i = 0; i < 4; i++) a.ref_stride[i] = p->ref_stride[i];
     a.geom = make_geom(p->H, p->W, p->K, p->downsample, p->img_scale, p->eps, p->correct_normalize, p->align_corners);
 
+    if (p->variant == EPI_VARIANT_PIPE && !pl.pipe) return fail(EPI_EINVAL, "pipe variant does not support this shape");
+    if (pl.pipe) {
+        const size_t elems = (size_t)p->N * p->C * p->H * p->W;
+        __nv_bfloat16 *planes = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_ref);
+        int *words = reinterpret_cast<int *>(ws + pl.off_counter);
+        const bool have_P = p->P_ref && p->P_src;
+        uint16_t *order = have_P ? reinterpret_cast<uint16_t *>(ws + pl.off_order) : nullptr;
+        epi::PairGeom *pg = reinterpret_cast<epi::PairGeom *>(ws + pl.off_geom);
+        e = epi::launch_stage(p->feat_ref, p->ref_stride, p->feat_src, p->src_stride, planes, p->P_ref, p->P_src, pg, order,
+                              reinterpret_cast<uint16_t *>(ws + pl.off_order_tmp), words, p->N, p->C, p->H, p->W, a.geom, st);
+        if (e != cudaSuccess) return fail(EPI_ECUDA, "operand staging launch failed: %s", cudaGetErrorString(e));
+        launches++;
+        a.ref_hi = planes; a.ref_lo = planes + elems; a.src_hi = planes + 2 * elems; a.src_lo = planes + 3 * elems;
+        a.order = order; a.pair_geom = pg; a.tile_counter = words; a.err_flag = words + 1;
+    } else
     if (p->variant == EPI_VARIANT_TILE && !pl.tile) return fail(EPI_EINVAL, "tile variant does not support this shape");
     if (p->variant == EPI_VARIANT_SECTOR && !pl.sector) return fail(EPI_EINVAL, "sector variant does not support this shape / injected locations");
     if (pl.tile) {
@@ -161,7 +197,7 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
         a.src_nhwc = p->feat_src;
     }
 
-    const bool z_tc = pl.has_z && pl.tile && epi::zgemm_supported(p->C);
+    const bool z_tc = pl.has_z && (pl.tile || pl.pipe) && epi::zgemm_supported(p->C);
     if (z_tc) {         // fused feature leaves the tile kernel as bf16 (hi, lo) planes: the A operand of the z GEMM
         a.out = nullptr;
         a.out_hi = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_prez);
@@ -185,7 +221,7 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
         if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
         cudaEventRecord(g_ev0, st);
     }
-    e = use_tile ? epi::launch_fusion_tile(a, st) : epi::launch_fusion_warp(a, st);
+    e = pl.pipe ? epi::launch_fusion_pipe(a, st) : (use_tile ? epi::launch_fusion_tile(a, st) : epi::launch_fusion_warp(a, st));
     if (e != cudaSuccess) return fail(EPI_ECUDA, "fusion kernel launch failed: %s", cudaGetErrorString(e));
     if (g_timing) { cudaEventRecord(g_ev1, st); g_timing_valid = 1; }
     launches++;

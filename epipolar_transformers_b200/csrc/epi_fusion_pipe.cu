@@ -1,0 +1,740 @@
+// epi_fusion_pipe.cu — the fused epipolar attention kernel (default): warp-specialised, mbarrier-pipelined,
+// tcgen05/TMEM.  One persistent CTA per SM, 23 warps:
+//
+//   warps  0-15  workers   scores TMEM -> table, 4-tap interpolation, ==0 mask, softmax over K (warp shuffles),
+//                          attn / corr_pos / sample_locs, β scatter, β -> bf16 (hi, lo) panels, epilogue TMEM -> global
+//   warps 16-17  setup     next work item: pixel list (sector order), epipolar line end points, union bitmap of the
+//                          bilinear taps of the item's pixels, prefix ranks, row list for the gathers
+//   warps 18-21  gather    16-byte cp.async (LDGSTS) of query rows and source-feature rows (bf16 hi/lo planes, pixel-major)
+//                          into 128-byte-swizzled shared-memory panels; completion through cp.async.mbarrier.arrive
+//                          (TMA tile::gather4 was measured at 7.5 B/clk/SM — profiles/gather4_probe_r2.txt — 5x too slow)
+//   warp  22     MMA       tcgen05.mma issue (one lane): GEMM1 S = F·Qᵀ and GEMM2 Oᵀ = Fᵀ·βᵀ, tcgen05.commit -> mbarriers
+//
+// Maths (identical to epi_fusion_tile.cu, restating /root/reference/modeling/layers/epipolar.py:199,210 grid_sample taps,
+// :295-307 similarity / ==0 mask / scale / softmax, :237-243 arg-max + weighted sum, :323-418 geometry):
+//   sim_k = Σ_t w_kt · (q · f[p_t])        out = Σ_p β_p · f[p],   β_p = Σ_{k,t→p} a_k w_kt
+// over the UNION of source pixels touched by the item's ≤32 epipolar lines (D ≤ 256 rows; items whose union is larger
+// are split by the setup warps).  Operands are bf16 (hi, lo) pairs: hi·hi + hi·lo + lo·hi, fp32 accumulation in TMEM.
+//
+// Pipeline: item j+1's gather + GEMM1 run while the workers are in item j's softmax phase; GEMM2(j) runs during
+// the workers' phase of item j+1; S and O accumulators are double-buffered in the 512 TMEM columns; the feature stages
+// are a 3-deep ring of 32 KB filled by the gather warps.  The only CTA-wide barriers are two 512-thread named barriers per item
+// among the workers; everything else is mbarrier producer/consumer hand-off.
+#include <cuda_bf16.h>
+
+#include "epi_kernels.cuh"
+#include "epi_umma.cuh"
+
+namespace epi {
+using namespace umma;
+
+namespace pipe {
+constexpr int P = 32;              // reference pixels per work item (MMA N = 2P: hi | lo stacked)
+constexpr int CHUNK = 128;         // union rows per GEMM1 accumulator (MMA M)
+constexpr int DMAX = 256;          // max union rows per item (two chunks)
+constexpr int NWORK = 16;          // worker warps
+constexpr int NT_WORK = NWORK * 32;
+constexpr int W_SETUP = 16, W_GATHER = 18, W_MMA = 22;
+constexpr int NGATHER = 128;       // gather threads
+constexpr int NT_ALL = 736;
+constexpr int MAXWORDS = 512;      // bitmap words: H*W <= 16384
+constexpr int MAXKPL = 4;          // samples per lane: K <= 128
+constexpr int NSTAGE = 3;
+constexpr int NDESC = 3;
+constexpr float FIX = 1073741824.0f;           // 2^30 fixed point for the β scatter (bit-reproducible)
+
+constexpr uint32_t STAGE_BYTES = 32768;        // GEMM1: [plane][128 rows x 128 B]; GEMM2: [plane][2 panels][64 rows x 128 B]
+constexpr uint32_t PLANE_BYTES = 16384;
+constexpr uint32_t PANEL_B2 = 8192;            // stacked B panel: 64 rows x 128 B (rows 0-31 hi, 32-63 lo)
+constexpr uint32_t OFF_STAGE = 0;
+constexpr uint32_t OFF_Q = NSTAGE * STAGE_BYTES;           // 4 stacked panels
+constexpr uint32_t OFF_BETA = OFF_Q + 4 * PANEL_B2;        // 4 stacked panels (256 d)
+constexpr uint32_t OFF_TABLE = OFF_BETA + 4 * PANEL_B2;    // [32][DMAX] fp32 scores, then int32 β
+constexpr uint32_t OFF_DESC = OFF_TABLE + P * DMAX * 4;
+
+struct Desc {                      // one work item, written by the setup warps
+    uint32_t bitmap[MAXWORDS];
+    uint16_t prefix[MAXWORDS];
+    uint16_t idx[DMAX];            // union rank -> source pixel (padded to a multiple of 16 with a valid row)
+    float4 ends[P];                // line end points in image coordinates (fused geometry)
+    uint32_t pix[P];               // y << 16 | x, 0xFFFFFFFF = no pixel
+    PairGeom geom;
+    int tile;                      // < 0: no more work
+    int n, g0, gn, D;
+    int pad[3];
+};
+constexpr uint32_t DESC_BYTES = (sizeof(Desc) + 127) / 128 * 128;
+constexpr uint32_t OFF_CTRL = OFF_DESC + NDESC * DESC_BYTES;
+
+struct Ctrl {
+    uint64_t desc_full[NDESC], desc_free[NDESC];
+    uint64_t q_full, q_empty;
+    uint64_t f_full[NSTAGE], f_empty[NSTAGE];
+    uint64_t s_full[2], s_empty[2];
+    uint64_t beta_full;
+    uint64_t o_full[2], o_empty[2];
+    uint32_t tmem_base;
+    int stack[16];
+    int sp;
+    int cur;                       // item being built: g0 | gn << 8
+    int cur_tile;
+    int total;
+    int done;
+};
+constexpr uint32_t SMEM_BYTES = OFF_CTRL + ((sizeof(Ctrl) + 127) / 128 * 128);
+constexpr uint32_t SMEM_ALLOC = SMEM_BYTES + 1024;         // 1024-byte alignment slack
+static_assert(SMEM_ALLOC <= 232448 - 2048, "keep head-room below the 227 KB opt-in limit");
+
+constexpr uint32_t TMEM_COLS = 512;
+constexpr uint32_t TMEM_S = 0;       // 2 buffers x 2 chunks x 64 columns
+constexpr uint32_t TMEM_O = 256;     // 2 buffers x 2 channel halves x 64 columns
+
+__device__ __forceinline__ void named_bar(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// Bounded mbarrier wait: a protocol bug must never hang the GPU.  On timeout the error word is set and the whole CTA
+// is torn down by __trap() (the launch fails with a sticky error instead of a hung box).
+__device__ __forceinline__ void wait_n(uint64_t *bar, uint32_t n) {
+    const uint32_t parity = n & 1u;
+    for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
+        if (it > (1u << 24)) __trap();
+}
+
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, float *v) {
+    uint32_t *r = reinterpret_cast<uint32_t *>(v);
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr)
+                 : "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo_elem, hi_elem);
+    return *reinterpret_cast<uint32_t *>(&v);
+}
+__device__ __forceinline__ void split8(const float *f, uint4 &hi, uint4 &lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+        const __nv_bfloat162 hv = __floats2bfloat162_rn(f[2 * u], f[2 * u + 1]);
+        const float2 hf = __bfloat1622float2(hv);
+        h[u] = *reinterpret_cast<const uint32_t *>(&hv);
+        l[u] = pack_bf16x2(f[2 * u] - hf.x, f[2 * u + 1] - hf.y);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+}  // namespace pipe
+
+using namespace pipe;
+
+template <int KPL>
+__global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const FusionArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    float *table = reinterpret_cast<float *>(smem + OFF_TABLE);
+    Ctrl &ct = *reinterpret_cast<Ctrl *>(smem + OFF_CTRL);
+    auto desc_at = [&](int j) -> Desc & { return *reinterpret_cast<Desc *>(smem + OFF_DESC + (uint32_t)(j % NDESC) * DESC_BYTES); };
+
+    const int C = a.C, K = a.geom.K, H = a.geom.H, W = a.geom.W, HW = H * W;
+    const int tiles_per_item = (HW + P - 1) / P;
+    const int total_tiles = a.N * tiles_per_item;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nwords = (HW + 31) >> 5;
+    const int NH = (C + 127) >> 7;                  // channel halves of 128 (GEMM2 M)
+    const int NP = (C + 63) >> 6;                   // 64-channel panels
+    const GeomCfg gc = a.geom;
+    const int NHW = a.N * HW;                       // plane stride (rows) of the operand buffer [ref_hi|ref_lo|src_hi|src_lo]
+
+    // ---------------- one-time setup ----------------
+    if (warp == 0) tmem_alloc(&ct.tmem_base, TMEM_COLS);
+    if (tid == 32) {
+        for (int i = 0; i < NDESC; i++) { mbar_init(&ct.desc_full[i], 1); mbar_init(&ct.desc_free[i], 2); }
+        mbar_init(&ct.q_full, NGATHER); mbar_init(&ct.q_empty, 1);
+        for (int i = 0; i < NSTAGE; i++) { mbar_init(&ct.f_full[i], NGATHER); mbar_init(&ct.f_empty[i], 1); }
+        for (int i = 0; i < 2; i++) {
+            mbar_init(&ct.s_full[i], 1); mbar_init(&ct.s_empty[i], 1);
+            mbar_init(&ct.o_full[i], 1); mbar_init(&ct.o_empty[i], NWORK);
+        }
+        mbar_init(&ct.beta_full, NWORK);
+        ct.sp = 0; ct.done = 0;
+        mbar_fence_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = ct.tmem_base;
+
+    // sample k of pixel i of item d: normalised location (fused geometry or injected locations)
+    auto sample_loc = [&](const Desc &d, int i, int k, float &gx, float &gy) {
+        if (a.locs_in) {
+            const uint32_t p = d.pix[i];
+            const float2 l = __ldg(reinterpret_cast<const float2 *>(a.locs_in) + ((size_t)k * a.N + d.n) * HW + (p >> 16) * W + (p & 0xffffu));
+            gx = l.x; gy = l.y;
+        } else {
+            const float4 e = d.ends[i];
+            const float t = (float)k / (float)(K - 1);
+            gx = img2grid_x(e.x + (e.z - e.x) * t, gc);
+            gy = img2grid_y(e.y + (e.w - e.y) * t, gc);
+        }
+    };
+
+    if (warp < NWORK) {
+        // =====================================================================================================
+        // WORKERS
+        // =====================================================================================================
+        const float sl2 = a.softmax_scale * 1.4426950408889634f;
+        const uint32_t tq = (uint32_t)((warp & 3) * 32) << 16;          // this warp's TMEM lane quadrant
+        uint8_t *bb = smem + OFF_BETA;
+
+        // epilogue of item j (accumulator buffer j & 1): fused feature TMEM -> global
+        auto epilogue = [&](int j) {
+            const Desc &d = desc_at(j);
+            const int h = (warp >> 2) & 1, ph = warp >> 3;
+            const int c = h * 128 + (warp & 3) * 32 + lane;
+            if (h < NH) {
+                float v[16], v2[16];
+                const uint32_t col = TMEM_O + (uint32_t)(j & 1) * 128u + (uint32_t)h * 64u + (uint32_t)ph * 16u;
+                tmem_ld_32x16(tmem + tq + col, v);
+                tmem_ld_32x16(tmem + tq + col + 32u, v2);
+                tmem_ld_wait();
+                if (c < C) {
+#pragma unroll
+                    for (int ii = 0; ii < 16; ii++) {
+                        const int i = ph * 16 + ii;
+                        const uint32_t p = d.pix[i];
+                        if (i < d.g0 || i >= d.g0 + d.gn || p == 0xFFFFFFFFu) continue;
+                        const int y = (int)(p >> 16), x = (int)(p & 0xffffu);
+                        float o = d.D > 0 ? v[ii] + v2[ii] : 0.f;        // D == 0: every sample masked, zero vectors
+                        if (a.out_hi) {
+                            const __nv_bfloat16 hv = __float2bfloat16_rn(o);
+                            const size_t off = ((size_t)d.n * HW + y * W + x) * C + c;
+                            a.out_hi[off] = hv;
+                            a.out_lo[off] = __float2bfloat16_rn(o - __bfloat162float(hv));
+                        } else {
+                            if (a.add_ref)
+                                o += __ldg(a.feat_ref + (int64_t)d.n * a.ref_stride[0] + (int64_t)c * a.ref_stride[1] + (int64_t)y * a.ref_stride[2] + (int64_t)x * a.ref_stride[3]);
+                            a.out[(int64_t)d.n * a.out_stride[0] + (int64_t)c * a.out_stride[1] + (int64_t)y * a.out_stride[2] + (int64_t)x * a.out_stride[3]] = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ct.o_empty[j & 1]);
+        };
+
+        int j = 0;
+        for (;; j++) {
+            named_bar(1, NT_WORK);                        // everyone is done with item j-1's table and item j-2's epilogue
+            if (tid == 0 && j >= 2) mbar_arrive(&ct.desc_free[(j - 2) % NDESC]);
+            wait_n(&ct.desc_full[j % NDESC], (uint32_t)(j / NDESC));
+            const Desc &d = desc_at(j);
+            if (d.tile < 0) break;
+            const int D = d.D, n = d.n, g0 = d.g0, gn = d.gn;
+            const int nch = (D + CHUNK - 1) / CHUNK;
+
+            // ---------------- B1: scores TMEM -> table[i][rank] ----------------
+            wait_n(&ct.s_full[j & 1], (uint32_t)(j >> 1));
+            tc_fence_after();
+            {
+                const int c = warp >> 2;
+                if (c < nch) {
+                    float v[32], v2[32];
+                    const uint32_t col = TMEM_S + (uint32_t)(j & 1) * 128u + (uint32_t)c * 64u;
+                    tmem_ld_32x32(tmem + tq + col, v);
+                    tmem_ld_32x32(tmem + tq + col + 32u, v2);
+                    tmem_ld_wait();
+                    const int r = c * CHUNK + (warp & 3) * 32 + lane;
+                    if (r < D) {
+#pragma unroll
+                        for (int i = 0; i < P; i++) table[i * DMAX + r] = v[i] + v2[i];
+                    }
+                }
+            }
+            tc_fence_before();
+            named_bar(1, NT_WORK);
+            if (tid == 0) mbar_arrive(&ct.s_empty[j & 1]);
+
+            // ---------------- B2: interpolate scores, softmax over K, outputs, β scatter ----------------
+            auto rank_of = [&](int pix) { return (int)d.prefix[pix >> 5] + __popc(d.bitmap[pix >> 5] & ((1u << (pix & 31)) - 1u)); };
+            {
+                constexpr int PW = P / NWORK;                          // 2 pixels per warp, interleaved for ILP; lane <-> sample
+                float x[PW][KPL], gxs[PW][KPL], gys[PW][KPL], tw[PW][KPL][4];
+                uint32_t rk[PW][KPL][2];
+                bool act[PW];
+                float mx[PW];
+                int py[PW], px[PW];
+#pragma unroll
+                for (int u = 0; u < PW; u++) {
+                    const int i = warp + u * NWORK;
+                    const uint32_t p = d.pix[i];
+                    act[u] = i >= g0 && i < g0 + gn && p != 0xFFFFFFFFu;
+                    py[u] = (int)(p >> 16); px[u] = (int)(p & 0xffffu);
+                    mx[u] = -INFINITY;
+#pragma unroll
+                    for (int jj = 0; jj < KPL; jj++) {
+                        const int k = jj * 32 + lane;
+                        x[u][jj] = -INFINITY; gxs[u][jj] = 0.f; gys[u][jj] = 0.f; rk[u][jj][0] = rk[u][jj][1] = 0u;
+#pragma unroll
+                        for (int tp = 0; tp < 4; tp++) tw[u][jj][tp] = 0.f;
+                        if (act[u] && k < K) {
+                            float gx, gy;
+                            sample_loc(d, i, k, gx, gy);
+                            gxs[u][jj] = gx; gys[u][jj] = gy;
+                            if (a.locs_out)
+                                reinterpret_cast<float2 *>(a.locs_out)[((size_t)k * a.N + n) * HW + py[u] * W + px[u]] = make_float2(gx, gy);
+                            const Taps t = make_taps(gx, gy, H, W, gc.align);
+                            float sim = 0.f;
+                            if (t.any) {
+                                uint32_t r[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                                for (int tp = 0; tp < 4; tp++)
+                                    if (t.w[tp] != 0.f) {
+                                        r[tp] = (uint32_t)rank_of((t.y0 + (tp >> 1)) * W + t.x0 + (tp & 1));
+                                        tw[u][jj][tp] = t.w[tp];
+                                        sim = fmaf(t.w[tp], table[i * DMAX + r[tp]], sim);
+                                    }
+                                rk[u][jj][0] = r[0] | (r[1] << 16); rk[u][jj][1] = r[2] | (r[3] << 16);
+                            }
+                            if (sim == 0.f) sim = kMasked;                      // epipolar.py:298
+                            x[u][jj] = sim * sl2;
+                            mx[u] = fmaxf(mx[u], x[u][jj]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int u = 0; u < PW; u++) mx[u] = fmaxf(mx[u], __shfl_xor_sync(0xffffffffu, mx[u], o));
+                float sum[PW];
+#pragma unroll
+                for (int u = 0; u < PW; u++) {
+                    sum[u] = 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < KPL; jj++) { x[u][jj] = (act[u] && jj * 32 + lane < K) ? exp2f(x[u][jj] - mx[u]) : 0.f; sum[u] += x[u][jj]; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                    for (int u = 0; u < PW; u++) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
+#pragma unroll
+                for (int u = 0; u < PW; u++) {
+                    if (!act[u]) continue;                              // warp-uniform
+                    const int i = warp + u * NWORK;
+                    const float inv = 1.f / sum[u];
+                    float best_v = -1.f, best_gx = 0.f, best_gy = 0.f;
+                    int best_k = 0x7fffffff;
+                    float *ab = a.attn ? a.attn + (size_t)n * K * HW + py[u] * W + px[u] : nullptr;
+#pragma unroll
+                    for (int jj = 0; jj < KPL; jj++) {
+                        const int k = jj * 32 + lane;
+                        x[u][jj] *= inv;
+                        if (k < K) {
+                            if (ab) ab[(size_t)k * HW] = x[u][jj];
+                            if (x[u][jj] > best_v) { best_v = x[u][jj]; best_k = k; best_gx = gxs[u][jj]; best_gy = gys[u][jj]; }
+                        }
+                    }
+                    if (a.corr_pos) {                                   // first maximum, like torch.argmax
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+                            const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+                            const float ogx = __shfl_xor_sync(0xffffffffu, best_gx, o), ogy = __shfl_xor_sync(0xffffffffu, best_gy, o);
+                            if (ov > best_v || (ov == best_v && ok < best_k)) { best_v = ov; best_k = ok; best_gx = ogx; best_gy = ogy; }
+                        }
+                        if (lane == 0)
+                            reinterpret_cast<float2 *>(a.corr_pos)[(size_t)n * HW + py[u] * W + px[u]] =
+                                make_float2(grid2corr(best_gx, W, gc.correct), grid2corr(best_gy, H, gc.correct));
+                    }
+                    // β row: zero, then deterministic fixed-point scatter of a_k·w_kt
+                    int *trow = reinterpret_cast<int *>(table + i * DMAX);
+                    __syncwarp();
+                    for (int r = lane; r < D; r += 32) trow[r] = 0;
+                    __syncwarp();
+#pragma unroll
+                    for (int jj = 0; jj < KPL; jj++) {
+                        if (jj * 32 + lane < K) {
+#pragma unroll
+                            for (int tp = 0; tp < 4; tp++)
+                                if (tw[u][jj][tp] != 0.f) {
+                                    const uint32_t r = (rk[u][jj][tp >> 1] >> ((tp & 1) * 16)) & 0xffffu;
+                                    atomicAdd(&trow[r], __float2int_rn(x[u][jj] * tw[u][jj][tp] * FIX));
+                                }
+                        }
+                    }
+                }
+                __syncwarp();
+
+                // ---------------- β rows of this warp's pixels -> bf16 (hi, lo) stacked K-major panels ----------------
+                if (j >= 1) wait_n(&ct.o_full[(j - 1) & 1], (uint32_t)((j - 1) >> 1));   // GEMM2(j-1) has consumed the β panels
+#pragma unroll
+                for (int u = 0; u < PW; u++) {
+                    const int i = warp + u * NWORK;
+                    const int *trow = reinterpret_cast<const int *>(table + i * DMAX);
+                    float f[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e++) {
+                        const int r = lane * 8 + e;
+                        f[e] = (act[u] && r < D) ? (float)trow[r] * (1.0f / FIX) : 0.f;
+                    }
+                    uint4 hi, lo;
+                    split8(f, hi, lo);
+                    const uint32_t off = (uint32_t)(lane >> 3) * PANEL_B2 + (uint32_t)i * 128u + (uint32_t)(((lane & 7) ^ (i & 7)) << 4);
+                    *reinterpret_cast<uint4 *>(bb + off) = hi;
+                    *reinterpret_cast<uint4 *>(bb + 4096 + off) = lo;
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&ct.beta_full);
+            }
+            // ---------------- epilogue of the previous item (its GEMM2 ran during this item's softmax) ----------------
+            if (j >= 1) { tc_fence_after(); epilogue(j - 1); }
+        }
+        if (j >= 1) {                                   // drain
+            wait_n(&ct.o_full[(j - 1) & 1], (uint32_t)((j - 1) >> 1));
+            tc_fence_after();
+            epilogue(j - 1);
+        }
+    } else if (warp < W_GATHER) {
+        // =====================================================================================================
+        // SETUP (2 warps): build work items
+        // =====================================================================================================
+        const int st = tid - W_SETUP * 32;                 // 0..63
+        const int sw = warp - W_SETUP;
+        int claimed = 0;
+        for (int j = 0;; j++) {
+            Desc &d = desc_at(j);
+            if (j >= NDESC) wait_n(&ct.desc_free[j % NDESC], (uint32_t)(j / NDESC - 1));
+            bool done = false;
+            while (true) {
+                // ---- next group: pop the split stack or claim a new tile ----
+                if (st == 0) {
+                    if (ct.sp == 0) {
+                        int tile;
+                        if (claimed == 0) tile = (int)blockIdx.x;
+                        else tile = a.tile_counter ? (int)gridDim.x + atomicAdd(a.tile_counter, 1) : (int)blockIdx.x + claimed * (int)gridDim.x;
+                        claimed++;
+                        if (tile < total_tiles) { ct.cur_tile = tile; ct.stack[0] = 0 | (P << 8); ct.sp = 1; }
+                        else ct.done = 1;
+                    }
+                    if (!ct.done) ct.cur = ct.stack[--ct.sp];
+                }
+                named_bar(2, 64);
+                if (ct.done) { done = true; break; }
+                const int tile = ct.cur_tile, g0 = ct.cur & 0xff, gn = ct.cur >> 8;
+                const int n = tile / tiles_per_item, trem = tile % tiles_per_item;
+                if (st < P) {
+                    const int e = trem * P + st;
+                    unsigned p = 0xFFFFu;
+                    if (e < HW) p = a.order ? (unsigned)a.order[(size_t)n * HW + e] : (unsigned)e;
+                    d.pix[st] = (e < HW) ? ((uint32_t)(p / W) << 16 | (uint32_t)(p % W)) : 0xFFFFFFFFu;
+                }
+                if (st == 32) { d.tile = tile; d.n = n; d.g0 = g0; d.gn = gn; }
+                if (st == 33 && !a.locs_in) d.geom = a.pair_geom[n];
+                for (int w = st; w < nwords; w += 64) d.bitmap[w] = 0u;
+                named_bar(2, 64);
+                if (st < P) {
+                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const uint32_t p = d.pix[st];
+                    if (p != 0xFFFFFFFFu && !a.locs_in)
+                        line_endpoints(d.geom, gc, pix2coord((int)(p & 0xffffu), gc.ds, gc.r), pix2coord((int)(p >> 16), gc.ds, gc.r), e.x, e.y, e.z, e.w);
+                    d.ends[st] = e;
+                }
+                named_bar(2, 64);
+                // ---- union of the in-bounds taps: lane <-> sample (consecutive samples fall into different words) ----
+                for (int i = g0 + sw; i < g0 + gn; i += 2) {
+                    if (d.pix[i] == 0xFFFFFFFFu) continue;
+                    for (int k = lane; k < K; k += 32) {
+                        float gx, gy;
+                        sample_loc(d, i, k, gx, gy);
+                        const Taps t = make_taps(gx, gy, H, W, gc.align);
+                        if (t.any) {
+#pragma unroll
+                            for (int tp = 0; tp < 4; tp++)
+                                if (t.w[tp] != 0.f) {
+                                    const int pix = (t.y0 + (tp >> 1)) * W + t.x0 + (tp & 1);
+                                    atomicOr(&d.bitmap[pix >> 5], 1u << (pix & 31));
+                                }
+                        }
+                    }
+                }
+                named_bar(2, 64);
+                // ---- exclusive prefix of popcounts (warp 0 of the pair; 16 words per lane max) ----
+                if (sw == 0) {
+                    const int per = (nwords + 31) >> 5;
+                    int cnt = 0;
+                    for (int q = 0; q < per; q++) { const int w = lane * per + q; if (w < nwords) cnt += __popc(d.bitmap[w]); }
+                    int incl = cnt;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+                    int run = incl - cnt;
+                    for (int q = 0; q < per; q++) {
+                        const int w = lane * per + q;
+                        if (w < nwords) { d.prefix[w] = (uint16_t)run; run += __popc(d.bitmap[w]); }
+                    }
+                    if (lane == 31) ct.total = incl;
+                }
+                named_bar(2, 64);
+                const int D = ct.total;
+                if (D > DMAX && gn > 1) {                 // split the group
+                    if (st == 0) {
+                        const int h1 = gn >> 1;
+                        ct.stack[ct.sp++] = (g0 + h1) | ((gn - h1) << 8);
+                        ct.stack[ct.sp++] = g0 | (h1 << 8);
+                    }
+                    named_bar(2, 64);
+                    continue;
+                }
+                const int Dc = D > DMAX ? 0 : D;          // a single pixel over DMAX cannot happen for supported shapes (host check)
+                if (D > DMAX && st == 0 && a.err_flag) atomicOr(a.err_flag, 1);
+                // ---- union list: idx[rank] = source pixel; pad to a multiple of 16 with a valid row ----
+                if (Dc > 0)
+                    for (int w = st; w < nwords; w += 64) {
+                        uint32_t bits = d.bitmap[w];
+                        int r = d.prefix[w];
+                        while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; d.idx[r++] = (uint16_t)(w * 32 + b); }
+                    }
+                named_bar(2, 64);
+                if (st < 16 && Dc > 0) { const int r = Dc + st; if (r < ((Dc + 15) & ~15)) d.idx[r] = d.idx[0]; }
+                if (st == 16) d.D = Dc;
+                named_bar(2, 64);
+                break;
+            }
+            if (done) {
+                if (st == 0) { d.tile = -1; mbar_arrive(&ct.desc_full[j % NDESC]); }
+                break;
+            }
+            if (st == 0) mbar_arrive(&ct.desc_full[j % NDESC]);
+        }
+    } else if (warp < W_MMA) {
+        // =====================================================================================================
+        // GATHER WARPS (128 threads): query rows and feature stages, 16-byte cp.async into swizzled panels.
+        // Thread t copies chunk j = t & 7 (8 channels) of rows (t >> 3) + 16·it; a row's 128-byte segment is read by 8
+        // consecutive lanes.  Completion: cp.async.mbarrier.arrive.noinc on the stage's mbarrier (count = 128 threads).
+        // =====================================================================================================
+        const int gt = tid - W_GATHER * 32, gj = gt & 7, gr = gt >> 3;
+        const __nv_bfloat16 *planes = a.ref_hi;          // [ref_hi | ref_lo | src_hi | src_lo], each [N*HW][C]
+        const size_t plane_elems = (size_t)NHW * C;
+        uint32_t qcount = 0, fcount = 0;
+        auto stage_acquire = [&]() -> uint8_t * {
+            const uint32_t s = fcount % NSTAGE;
+            if (fcount >= NSTAGE) wait_n(&ct.f_empty[s], fcount / NSTAGE - 1);
+            return smem + OFF_STAGE + s * STAGE_BYTES;
+        };
+        auto arrive_async = [&](uint64_t *bar) {
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+        };
+        auto gemm2_stages = [&](int jj) {
+            const Desc &d = desc_at(jj);
+            const int D16 = (d.D + 15) & ~15, nblk = (D16 + 63) >> 6;
+            const __nv_bfloat16 *src = planes + 2 * plane_elems + (size_t)d.n * HW * C;
+            for (int h = 0; h < NH; h++)
+                for (int blk = 0; blk < nblk; blk++) {
+                    uint8_t *stg = stage_acquire();
+                    const int rows = min(64, D16 - blk * 64);
+#pragma unroll
+                    for (int it = 0; it < 4; it++) {
+                        const int r = gr + 16 * it;
+                        if (r < rows) {
+                            const __nv_bfloat16 *row = src + (size_t)d.idx[blk * 64 + r] * C;
+                            const uint32_t so = (uint32_t)r * 128u + (uint32_t)((gj ^ (r & 7)) << 4);
+#pragma unroll
+                            for (int pn = 0; pn < 2; pn++) {
+                                const int ch = (h * 2 + pn) * 64 + gj * 8;
+                                if (ch < C) {
+                                    cp_async16(stg + pn * 8192 + so, row + ch, true);
+                                    cp_async16(stg + PLANE_BYTES + pn * 8192 + so, row + plane_elems + ch, true);
+                                }
+                            }
+                        }
+                    }
+                    arrive_async(&ct.f_full[fcount % NSTAGE]);
+                    fcount++;
+                }
+        };
+        for (int j = 0;; j++) {
+            wait_n(&ct.desc_full[j % NDESC], (uint32_t)(j / NDESC));
+            const Desc &d = desc_at(j);
+            const bool last = d.tile < 0;
+            if (!last && d.D > 0) {
+                // ---- query rows of the item's pixels: stacked panels [hi 32 rows | lo 32 rows] x NP ----
+                if (qcount >= 1) wait_n(&ct.q_empty, qcount - 1);
+                {
+                    const __nv_bfloat16 *ref = planes + (size_t)d.n * HW * C;
+#pragma unroll
+                    for (int it = 0; it < 2; it++) {
+                        const int r = gr + 16 * it;
+                        const uint32_t p = d.pix[r];
+                        const __nv_bfloat16 *row = ref + (size_t)(p == 0xFFFFFFFFu ? 0 : (int)(p >> 16) * W + (int)(p & 0xffffu)) * C;
+                        const uint32_t so = (uint32_t)r * 128u + (uint32_t)((gj ^ (r & 7)) << 4);
+#pragma unroll
+                        for (int kp = 0; kp < 4; kp++) {
+                            const int ch = kp * 64 + gj * 8;
+                            if (kp < NP) {                  // channels beyond C are zero-filled: they are part of the MMA K range
+                                const bool ok = ch < C;
+                                cp_async16(smem + OFF_Q + kp * PANEL_B2 + so, ok ? row + ch : row, ok);
+                                cp_async16(smem + OFF_Q + kp * PANEL_B2 + 4096 + so, ok ? row + plane_elems + ch : row, ok);
+                            }
+                        }
+                    }
+                }
+                arrive_async(&ct.q_full);
+                qcount++;
+                // ---- GEMM1 stages: (chunk, 64-channel panel) ----
+                const int D16 = (d.D + 15) & ~15, nch = (d.D + CHUNK - 1) / CHUNK;
+                const __nv_bfloat16 *src = planes + 2 * plane_elems + (size_t)d.n * HW * C;
+                for (int c = 0; c < nch; c++) {
+                    const int rows = min(CHUNK, D16 - c * CHUNK);
+                    for (int kp = 0; kp < NP; kp++) {
+                        uint8_t *stg = stage_acquire();
+                        const int ch = kp * 64 + gj * 8;
+#pragma unroll
+                        for (int it = 0; it < 8; it++) {
+                            const int r = gr + 16 * it;
+                            if (r < rows) {
+                                const bool ok = ch < C;
+                                const __nv_bfloat16 *row = src + (size_t)d.idx[c * CHUNK + r] * C + (ok ? ch : 0);
+                                const uint32_t so = (uint32_t)r * 128u + (uint32_t)((gj ^ (r & 7)) << 4);
+                                cp_async16(stg + so, row, ok);
+                                cp_async16(stg + PLANE_BYTES + so, row + plane_elems, ok);
+                            }
+                        }
+                        arrive_async(&ct.f_full[fcount % NSTAGE]);
+                        fcount++;
+                    }
+                }
+            }
+            if (j >= 1) {
+                if (desc_at(j - 1).D > 0) gemm2_stages(j - 1);
+                named_bar(3, NGATHER);                      // every gather thread has read item j-1's row list
+                if (gt == 0) mbar_arrive(&ct.desc_free[(j - 1) % NDESC]);
+            }
+            if (last) break;
+        }
+    } else {
+        // =====================================================================================================
+        // MMA ISSUER
+        // =====================================================================================================
+        uint32_t qcount = 0, fcount = 0;
+        const uint32_t sq = smem_u32(smem + OFF_Q), sb = smem_u32(smem + OFF_BETA);
+        auto gemm2 = [&](int jj) {
+            const Desc &d = desc_at(jj);
+            wait_n(&ct.beta_full, (uint32_t)jj);
+            if (jj >= 2) wait_n(&ct.o_empty[jj & 1], (uint32_t)((jj >> 1) - 1));
+            tc_fence_after();
+            if (d.D > 0) {
+                const int D16 = (d.D + 15) & ~15, nblk = (D16 + 63) >> 6;
+                const uint32_t idesc64 = make_idesc_bf16(128, 2 * P, 1, 0), idesc32 = make_idesc_bf16(128, P, 1, 0);
+                for (int h = 0; h < NH; h++)
+                    for (int blk = 0; blk < nblk; blk++) {
+                        const uint32_t s = fcount % NSTAGE;
+                        wait_n(&ct.f_full[s], fcount / NSTAGE);
+                        fence_proxy_async_smem();           // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
+                        tc_fence_after();
+                        if (lane == 0) {
+                            const uint32_t sa = smem_u32(smem + OFF_STAGE + s * STAGE_BYTES);
+                            const uint32_t dst = tmem + TMEM_O + (uint32_t)(jj & 1) * 128u + (uint32_t)h * 64u;
+                            const int nk = min(4, (D16 - blk * 64) >> 4);
+                            for (int kk = 0; kk < nk; kk++) {
+                                const uint64_t a_hi = make_smem_desc(sa + kk * 2048, 8192, 1024), a_lo = make_smem_desc(sa + PLANE_BYTES + kk * 2048, 8192, 1024);
+                                const uint64_t b = make_smem_desc(sb + blk * PANEL_B2 + kk * 32, 16, 1024);
+                                mma_bf16(dst, a_hi, b, idesc64, (blk | kk) ? 1u : 0u);      // [Fᵀ_hi·β_hi | Fᵀ_hi·β_lo]
+                                mma_bf16(dst, a_lo, b, idesc32, 1u);                        //  += Fᵀ_lo·β_hi
+                            }
+                            mma_commit(&ct.f_empty[s]);
+                        }
+                        __syncwarp();
+                        fcount++;
+                    }
+            }
+            if (lane == 0) mma_commit(&ct.o_full[jj & 1]);
+            __syncwarp();
+        };
+        for (int j = 0;; j++) {
+            wait_n(&ct.desc_full[j % NDESC], (uint32_t)(j / NDESC));
+            const Desc &d = desc_at(j);
+            const bool last = d.tile < 0;
+            if (!last) {
+                if (j >= 2) wait_n(&ct.s_empty[j & 1], (uint32_t)((j >> 1) - 1));
+                tc_fence_after();
+                if (d.D > 0) {
+                    wait_n(&ct.q_full, qcount);
+                    fence_proxy_async_smem();
+                    const int nch = (d.D + CHUNK - 1) / CHUNK;
+                    const uint32_t idesc64 = make_idesc_bf16(128, 2 * P, 0, 0), idesc32 = make_idesc_bf16(128, P, 0, 0);
+                    for (int c = 0; c < nch; c++)
+                        for (int kp = 0; kp < NP; kp++) {
+                            const uint32_t s = fcount % NSTAGE;
+                            wait_n(&ct.f_full[s], fcount / NSTAGE);
+                            fence_proxy_async_smem();
+                            tc_fence_after();
+                            if (lane == 0) {
+                                const uint32_t sa = smem_u32(smem + OFF_STAGE + s * STAGE_BYTES);
+                                const uint32_t dst = tmem + TMEM_S + (uint32_t)(j & 1) * 128u + (uint32_t)c * 64u;
+#pragma unroll
+                                for (int ks = 0; ks < 4; ks++) {
+                                    const uint64_t a_hi = make_smem_desc(sa + ks * 32, 16, 1024), a_lo = make_smem_desc(sa + PLANE_BYTES + ks * 32, 16, 1024);
+                                    const uint64_t b = make_smem_desc(sq + kp * PANEL_B2 + ks * 32, 16, 1024);
+                                    mma_bf16(dst, a_hi, b, idesc64, (kp | ks) ? 1u : 0u);      // [F_hi·Q_hi | F_hi·Q_lo]
+                                    mma_bf16(dst, a_lo, b, idesc32, 1u);                      //  += F_lo·Q_hi
+                                }
+                                mma_commit(&ct.f_empty[s]);
+                            }
+                            __syncwarp();
+                            fcount++;
+                        }
+                    if (lane == 0) mma_commit(&ct.q_empty);
+                    qcount++;
+                }
+                if (lane == 0) mma_commit(&ct.s_full[j & 1]);
+                __syncwarp();
+            }
+            if (j >= 1) gemm2(j - 1);
+            if (last) break;
+        }
+    }
+
+    // ---------------- teardown ----------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+
+bool fusion_pipe_shape_ok(int C, int H, int W, int K, bool has_locs_in) {
+    if (C % 8 != 0 || C > 256 || C < 8) return false;
+    if (H * W > MAXWORDS * 32 || H * W > 65535) return false;
+    if (K > 32 * MAXKPL) return false;
+    // a single pixel's union must fit DMAX: 4 taps per sample, and (fused geometry) a straight line crosses at most
+    // H+W pixel rows/columns, 2 pixels wide, plus the footprint ends
+    const int single = has_locs_in ? 4 * K : (4 * K < 2 * (H + W) + 8 ? 4 * K : 2 * (H + W) + 8);
+    return single <= DMAX;
+}
+
+cudaError_t launch_fusion_pipe(const FusionArgs &a, cudaStream_t st) {
+    const int HW = a.geom.H * a.geom.W;
+    const int tiles = a.N * ((HW + P - 1) / P);
+    const int kpl = (a.geom.K + 31) / 32;
+    void (*kern)(const FusionArgs) = kpl <= 1 ? epi_fusion_pipe_kernel<1> : (kpl <= 2 ? epi_fusion_pipe_kernel<2> : epi_fusion_pipe_kernel<4>);
+    static thread_local int sms_cached = 0;
+    static thread_local bool attr_set[3] = {false, false, false};
+    const int ki = kpl <= 1 ? 0 : (kpl <= 2 ? 1 : 2);
+    if (!attr_set[ki]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_ALLOC);
+        if (e != cudaSuccess) return e;
+        attr_set[ki] = true;
+    }
+    if (!sms_cached) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms_cached, cudaDevAttrMultiProcessorCount, dev);
+        if (sms_cached <= 0) sms_cached = 148;
+    }
+    const int grid = tiles < sms_cached ? tiles : sms_cached;      // one persistent CTA per SM
+    kern<<<grid, NT_ALL, SMEM_ALLOC, st>>>(a);
+    return cudaGetLastError();
+}
+
+}  // namespace epi

@@ -22,6 +22,8 @@ struct FusionArgs {
     float softmax_scale;
     int add_ref;
     int *tile_counter;                        // zeroed by the staging kernel; dynamic tile scheduler of the tile kernel
+    const PairGeom *pair_geom;                // [N] per-pair constants (fp64-derived) written by the staging kernel — pipe kernel
+    int *err_flag;                            // device word OR-ed with 1 when a work item had to be dropped (never for supported shapes)
     GeomCfg geom;
 };
 
@@ -49,11 +51,17 @@ cudaError_t launch_zgemm(const ZGemmArgs &z, cudaStream_t st);
 
 cudaError_t launch_fusion_warp(const FusionArgs &a, cudaStream_t st);
 cudaError_t launch_fusion_tile(const FusionArgs &a, cudaStream_t st);
+cudaError_t launch_fusion_pipe(const FusionArgs &a, cudaStream_t st);
+bool fusion_pipe_shape_ok(int C, int H, int W, int K, bool has_locs_in);
 bool fusion_tile_supported(const FusionArgs &a);
 bool fusion_tile_shape_ok(int C, int H, int W, int K, bool has_locs_in);
 cudaError_t launch_sector_order(const float *P_ref, const float *P_src, uint16_t *order, int N, const GeomCfg &gc, cudaStream_t st);
 cudaError_t launch_split_planes(const float *src, const int64_t stride[4], __nv_bfloat16 *hi, __nv_bfloat16 *lo, int N, int C,
                                 int H, int W, int *zero_me, cudaStream_t st);
+
+cudaError_t launch_stage(const float *ref, const int64_t ref_stride[4], const float *src, const int64_t src_stride[4],
+                         __nv_bfloat16 *planes, const float *P_ref, const float *P_src, PairGeom *pair_geom, uint16_t *order,
+                         uint16_t *order_tmp, int *zero_words, int N, int C, int H, int W, const GeomCfg &gc, cudaStream_t st);
 
 cudaError_t launch_nchw_to_nhwc(const float *src, const int64_t stride[4], float *dst, int N, int C, int H, int W, cudaStream_t st);
 cudaError_t launch_z_epilogue(const ZArgs &z, cudaStream_t st);

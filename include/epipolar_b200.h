@@ -36,10 +36,11 @@ extern "C" {
 #define EPI_ECUDA (-3)        /* CUDA runtime error at launch (message has the cudaError string) */
 
 /* kernel variants (EpiFusionParams.variant) */
-#define EPI_VARIANT_AUTO 0    /* sector tiles when the shape allows and the geometry is fused, else block tiles, else warp */
+#define EPI_VARIANT_AUTO 0    /* pipelined kernel when the shape allows, else sector / block tiles, else warp */
 #define EPI_VARIANT_WARP 1    /* one warp per reference pixel, online softmax (baseline kernel) */
 #define EPI_VARIANT_TILE 2    /* tensor-core kernel, 4x8 pixel tiles: shared-memory staged source taps, score interpolation */
 #define EPI_VARIANT_SECTOR 3  /* tensor-core kernel, tiles of 32 pixels that share an epipolar line (sorted by epipolar angle) */
+#define EPI_VARIANT_PIPE 4    /* warp-specialised, mbarrier-pipelined tensor-core kernel over epipolar-sector work items (default) */
 
 typedef struct EpiFusionParams {
     /* ---- inputs ---------------------------------------------------------------------- */

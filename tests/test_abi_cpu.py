@@ -71,15 +71,19 @@ def test_workspace_plan(lib):
     p.feat_src = ctypes.addressof(buf)
     p.src_stride = (ctypes.c_int64 * 4)(256 * 4096, 4096, 64, 1)           # NCHW: needs staging
     m = 4 * 256 * 64 * 64 * 4
-    order = 4 * 4096 * 2                                                     # sector tiles: pixel order list (u16)
-    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 2 * m + 256 + order   # src planes + ref planes + counter + order
+    order = 4 * 4096 * 2                                                     # pixel order list (u16)
+    geom = 256                                                               # 4 pairs x 44 B of pair constants, 256-B granules
+    pipe = 2 * m + 256 + 2 * order + geom       # ref + src bf16 (hi, lo) planes, counter/error words, order + sort scratch
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == pipe
     p.z_weight_folded = ctypes.addressof(buf)
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == pipe + m      # + pre-z bf16 planes
+    p.variant = _lib.EPI_VARIANT_SECTOR
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 3 * m + 256 + order
     p.variant = _lib.EPI_VARIANT_TILE
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 2 * m + 256   # 4x8 block tiles: no ref planes / order list
     p.variant = _lib.EPI_VARIANT_AUTO
     p.src_stride = (ctypes.c_int64 * 4)(256 * 4096, 1, 64 * 256, 256)      # channels_last
-    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 3 * m + 256 + order   # tensor-core kernel stages bf16 (hi, lo) planes
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == pipe + m      # tensor-core kernels stage bf16 (hi, lo) planes
     p.variant = _lib.EPI_VARIANT_WARP
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == m             # warp kernel reads channels_last in place
 

@@ -13,7 +13,7 @@ for name in names:
     cfg, f1, f2, P1, P2, params = gc.build_inputs(name)
     spec = gc.CASES[name]
     res = {}
-    for variant in ("warp", "auto", "sector"):
+    for variant in ("warp", "pipe", "sector"):
         try:
             out, corr, attn, locs = epi.epipolar_fusion(dev(f1), dev(f2), dev(P1), dev(P2), K=spec["K"], downsample=cfg.BACKBONE.DOWNSAMPLE,
                 img_scale=cfg.DATASETS.IMAGE_RESIZE * cfg.DATASETS.PREDICT_RESIZE, correct_normalize=spec["correct"], want_locs=True, variant=variant)
@@ -23,7 +23,7 @@ for name in names:
             print(name, variant, "FAILED", repr(e)[:300]); res[variant] = None
     if res["warp"] is None: continue
     o = c_oracle.forward(cfg, f1, f2, P1, P2, locs=res["warp"][3])
-    for variant in ("warp", "auto", "sector"):
+    for variant in ("warp", "pipe", "sector"):
         if res[variant] is None: continue
         out, attn, corr, locs = res[variant]
         eo_ = np.abs(out - o["out"]).max() / max(np.abs(o["out"]).max(), 1e-30)
