@@ -31,15 +31,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, timers: bool = False) -> str:
+    """timers=True builds libepipolar_b200_timers.so with the in-kernel clock64 phase timers (developer tool)."""
+    if not timers and not force and not needs_build():
         return LIB
     nvcc = _nvcc()
     objs = []
     procs = []
+    lib = LIB.replace(".so", "_timers.so") if timers else LIB
     for s in SOURCES:
-        obj = os.path.join(CSRC, s.replace(".cu", ".o"))
+        obj = os.path.join(CSRC, s.replace(".cu", ".timers.o" if timers else ".o"))
         cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, s), "-o", obj]
+        if timers:
+            cmd[1:1] = ["-DEPI_PIPE_TIMERS", "-DEPI_TILE_TIMERS"]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
@@ -50,9 +54,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed on %s" % s)
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-lcudart"])
-    return LIB
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", lib, *objs, "-lcudart"])
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, timers="--timers" in sys.argv))

@@ -99,9 +99,14 @@ __device__ __forceinline__ float img2grid_x(float v, const GeomCfg &c) { return 
 __device__ __forceinline__ float img2grid_y(float v, const GeomCfg &c) { return fmaf(fmaf(v, c.inv_rds, c.off_ds), c.gsy, c.goy); }
 
 // normalised grid coordinate -> source feature-pixel coordinate (ATen grid_sampler unnormalize)
+// (explicit intrinsics: the union-marking code and the sampling code must produce bit-identical pixel coordinates, so
+// no step may be left to the compiler's FMA contraction)
 __device__ __forceinline__ float grid2pix(float g, int size, int align) {
-    return align ? (g + 1.f) * 0.5f * (float)(size - 1) : ((g + 1.f) * (float)size - 1.f) * 0.5f;
+    const float g1 = __fadd_rn(g, 1.f);
+    return align ? __fmul_rn(__fmul_rn(g1, 0.5f), (float)(size - 1)) : __fmul_rn(__fmaf_rn(g1, (float)size, -1.f), 0.5f);
 }
+// sample at parameter t in [0,1] on the segment (sx,sy)-(ex,ey) (image coordinates) -> normalised grid coordinates
+__device__ __forceinline__ float lerp_exact(float a, float b, float t) { return __fmaf_rn(__fsub_rn(b, a), t, a); }
 
 // de_normalize (multiview.py:39-57): grid coordinate -> feature px as the reference reports corr_pos
 __device__ __forceinline__ float grid2corr(float g, int size, int correct) {

@@ -1,14 +1,14 @@
 // epi_fusion_pipe.cu — the fused epipolar attention kernel (default): warp-specialised, mbarrier-pipelined,
-// tcgen05/TMEM.  One persistent CTA per SM, 23 warps:
+// tcgen05/TMEM.  One persistent CTA per SM, 25 warps:
 //
 //   warps  0-15  workers   scores TMEM -> table, 4-tap interpolation, ==0 mask, softmax over K (warp shuffles),
 //                          attn / corr_pos / sample_locs, β scatter, β -> bf16 (hi, lo) panels, epilogue TMEM -> global
-//   warps 16-17  setup     next work item: pixel list (sector order), epipolar line end points, union bitmap of the
+//   warps 16-19  setup     next work item: pixel list (sector order), epipolar line end points, union bitmap of the
 //                          bilinear taps of the item's pixels, prefix ranks, row list for the gathers
-//   warps 18-21  gather    16-byte cp.async (LDGSTS) of query rows and source-feature rows (bf16 hi/lo planes, pixel-major)
+//   warps 20-23  gather    16-byte cp.async (LDGSTS) of query rows and source-feature rows (bf16 hi/lo planes, pixel-major)
 //                          into 128-byte-swizzled shared-memory panels; completion through cp.async.mbarrier.arrive
 //                          (TMA tile::gather4 was measured at 7.5 B/clk/SM — profiles/gather4_probe_r2.txt — 5x too slow)
-//   warp  22     MMA       tcgen05.mma issue (one lane): GEMM1 S = F·Qᵀ and GEMM2 Oᵀ = Fᵀ·βᵀ, tcgen05.commit -> mbarriers
+//   warp  24     MMA       tcgen05.mma issue (one lane): GEMM1 S = F·Qᵀ and GEMM2 Oᵀ = Fᵀ·βᵀ, tcgen05.commit -> mbarriers
 //
 // Maths (identical to epi_fusion_tile.cu, restating /root/reference/modeling/layers/epipolar.py:199,210 grid_sample taps,
 // :295-307 similarity / ==0 mask / scale / softmax, :237-243 arg-max + weighted sum, :323-418 geometry):
@@ -34,9 +34,10 @@ constexpr int CHUNK = 128;         // union rows per GEMM1 accumulator (MMA M)
 constexpr int DMAX = 256;          // max union rows per item (two chunks)
 constexpr int NWORK = 16;          // worker warps
 constexpr int NT_WORK = NWORK * 32;
-constexpr int W_SETUP = 16, W_GATHER = 18, W_MMA = 22;
+constexpr int W_SETUP = 16, W_GATHER = 20, W_MMA = 24;
+constexpr int NSETUP = 128;        // setup threads
 constexpr int NGATHER = 128;       // gather threads
-constexpr int NT_ALL = 736;
+constexpr int NT_ALL = 800;
 constexpr int MAXWORDS = 512;      // bitmap words: H*W <= 16384
 constexpr int MAXKPL = 4;          // samples per lane: K <= 128
 constexpr int NSTAGE = 3;
@@ -49,8 +50,10 @@ constexpr uint32_t PANEL_B2 = 8192;            // stacked B panel: 64 rows x 128
 constexpr uint32_t OFF_STAGE = 0;
 constexpr uint32_t OFF_Q = NSTAGE * STAGE_BYTES;           // 4 stacked panels
 constexpr uint32_t OFF_BETA = OFF_Q + 4 * PANEL_B2;        // 4 stacked panels (256 d)
-constexpr uint32_t OFF_TABLE = OFF_BETA + 4 * PANEL_B2;    // [32][DMAX] fp32 scores, then int32 β
-constexpr uint32_t OFF_DESC = OFF_TABLE + P * DMAX * 4;
+constexpr int TP = 33;             // row pitch (floats) of the d-major score table T[rank][pixel]
+constexpr uint32_t OFF_TABLE = OFF_BETA + 4 * PANEL_B2;    // [DMAX][33] fp32 scores, then int32 β, then the epilogue's [32][256] transposition
+constexpr uint32_t OFF_RED = OFF_TABLE + DMAX * TP * 4;    // softmax / arg-max split-reduction scratch [4][16][32]
+constexpr uint32_t OFF_DESC = OFF_RED + 4 * NWORK * 32 * 4;
 
 struct Desc {                      // one work item, written by the setup warps
     uint32_t bitmap[MAXWORDS];
@@ -58,7 +61,6 @@ struct Desc {                      // one work item, written by the setup warps
     uint16_t idx[DMAX];            // union rank -> source pixel (padded to a multiple of 16 with a valid row)
     float4 ends[P];                // line end points in image coordinates (fused geometry)
     uint32_t pix[P];               // y << 16 | x, 0xFFFFFFFF = no pixel
-    PairGeom geom;
     int tile;                      // < 0: no more work
     int n, g0, gn, D;
     int pad[3];
@@ -129,6 +131,15 @@ __device__ __forceinline__ void split8(const float *f, uint4 &hi, uint4 &lo) {
 
 using namespace pipe;
 
+#ifdef EPI_PIPE_TIMERS
+__device__ unsigned long long g_pipe_timers[32];
+#define PT_DECL long long pt_prev = clock64()
+#define PT(slot) do { if (pt_on) { const long long t_ = clock64(); atomicAdd(&g_pipe_timers[slot], (unsigned long long)(t_ - pt_prev)); pt_prev = t_; } } while (0)
+#else
+#define PT_DECL do { } while (0)
+#define PT(slot) do { } while (0)
+#endif
+
 template <int KPL>
 __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const FusionArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -146,6 +157,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
     const int NP = (C + 63) >> 6;                   // 64-channel panels
     const GeomCfg gc = a.geom;
     const int NHW = a.N * HW;                       // plane stride (rows) of the operand buffer [ref_hi|ref_lo|src_hi|src_lo]
+    constexpr int KW = 2 * KPL;                     // samples per worker warp (k = warp + 16 jj)
 
     // ---------------- one-time setup ----------------
     if (warp == 0) tmem_alloc(&ct.tmem_base, TMEM_COLS);
@@ -166,78 +178,94 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
     tc_fence_after();
     const uint32_t tmem = ct.tmem_base;
 
-    // sample k of pixel i of item d: normalised location (fused geometry or injected locations)
-    auto sample_loc = [&](const Desc &d, int i, int k, float &gx, float &gy) {
-        if (a.locs_in) {
-            const uint32_t p = d.pix[i];
-            const float2 l = __ldg(reinterpret_cast<const float2 *>(a.locs_in) + ((size_t)k * a.N + d.n) * HW + (p >> 16) * W + (p & 0xffffu));
-            gx = l.x; gy = l.y;
-        } else {
-            const float4 e = d.ends[i];
-            const float t = (float)k / (float)(K - 1);
-            gx = img2grid_x(e.x + (e.z - e.x) * t, gc);
-            gy = img2grid_y(e.y + (e.w - e.y) * t, gc);
-        }
-    };
-
     if (warp < NWORK) {
         // =====================================================================================================
-        // WORKERS
+        // WORKERS (16 warps).  lane <-> pixel of the item, warp <-> samples k = warp, warp+16, ...  The score table is
+        // d-major, T[rank][pixel] with a 33-float row pitch: every access of a warp (32 pixels, nearly equal ranks) is
+        // bank-conflict free, the K-wide softmax is a 16-way split reduction through shared memory.
         // =====================================================================================================
         const float sl2 = a.softmax_scale * 1.4426950408889634f;
         const uint32_t tq = (uint32_t)((warp & 3) * 32) << 16;          // this warp's TMEM lane quadrant
         uint8_t *bb = smem + OFF_BETA;
+        float *red_max = reinterpret_cast<float *>(smem + OFF_RED);     // [16][32]
+        float *red_sum = red_max + NWORK * 32;
+        float *red_bv = red_sum + NWORK * 32;
+        int *red_bk = reinterpret_cast<int *>(red_bv + NWORK * 32);
+        int *Ti = reinterpret_cast<int *>(table);
+        float tkw[KW];                                                   // sample parameters of this warp
+#pragma unroll
+        for (int jj = 0; jj < KW; jj++) tkw[jj] = (float)(warp + NWORK * jj) / (float)(K - 1);
 
-        // epilogue of item j (accumulator buffer j & 1): fused feature TMEM -> global
+        // epilogue of item j (accumulator buffer j & 1): fused feature TMEM -> table (as [pixel][channel]) -> global
         auto epilogue = [&](int j) {
             const Desc &d = desc_at(j);
-            const int h = (warp >> 2) & 1, ph = warp >> 3;
-            const int c = h * 128 + (warp & 3) * 32 + lane;
-            if (h < NH) {
-                float v[16], v2[16];
-                const uint32_t col = TMEM_O + (uint32_t)(j & 1) * 128u + (uint32_t)h * 64u + (uint32_t)ph * 16u;
-                tmem_ld_32x16(tmem + tq + col, v);
-                tmem_ld_32x16(tmem + tq + col + 32u, v2);
-                tmem_ld_wait();
-                if (c < C) {
+            {
+                const int h = (warp >> 2) & 1, ph = warp >> 3;
+                const int c = h * 128 + (warp & 3) * 32 + lane;
+                if (h < NH) {
+                    float v[16], v2[16];
+                    const uint32_t col = TMEM_O + (uint32_t)(j & 1) * 128u + (uint32_t)h * 64u + (uint32_t)ph * 16u;
+                    tmem_ld_32x16(tmem + tq + col, v);
+                    tmem_ld_32x16(tmem + tq + col + 32u, v2);
+                    tmem_ld_wait();
 #pragma unroll
-                    for (int ii = 0; ii < 16; ii++) {
-                        const int i = ph * 16 + ii;
-                        const uint32_t p = d.pix[i];
-                        if (i < d.g0 || i >= d.g0 + d.gn || p == 0xFFFFFFFFu) continue;
-                        const int y = (int)(p >> 16), x = (int)(p & 0xffffu);
-                        float o = d.D > 0 ? v[ii] + v2[ii] : 0.f;        // D == 0: every sample masked, zero vectors
-                        if (a.out_hi) {
-                            const __nv_bfloat16 hv = __float2bfloat16_rn(o);
-                            const size_t off = ((size_t)d.n * HW + y * W + x) * C + c;
-                            a.out_hi[off] = hv;
-                            a.out_lo[off] = __float2bfloat16_rn(o - __bfloat162float(hv));
-                        } else {
-                            if (a.add_ref)
-                                o += __ldg(a.feat_ref + (int64_t)d.n * a.ref_stride[0] + (int64_t)c * a.ref_stride[1] + (int64_t)y * a.ref_stride[2] + (int64_t)x * a.ref_stride[3]);
-                            a.out[(int64_t)d.n * a.out_stride[0] + (int64_t)c * a.out_stride[1] + (int64_t)y * a.out_stride[2] + (int64_t)x * a.out_stride[3]] = o;
+                    for (int ii = 0; ii < 16; ii++) table[(ph * 16 + ii) * 256 + c] = d.D > 0 ? v[ii] + v2[ii] : 0.f;   // D == 0: all masked
+                }
+            }
+            tc_fence_before();
+            named_bar(1, NT_WORK);
+            if (lane == 0 && warp < NWORK) mbar_arrive(&ct.o_empty[j & 1]);
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int i = warp * 2 + u;
+                const uint32_t p = d.pix[i];
+                if (i < d.g0 || i >= d.g0 + d.gn || p == 0xFFFFFFFFu) continue;          // warp-uniform
+                const int y = (int)(p >> 16), x = (int)(p & 0xffffu);
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const int c0 = hh * 128 + lane * 4;
+                    if (c0 >= C) continue;
+                    const float4 o = *reinterpret_cast<const float4 *>(table + i * 256 + c0);
+                    if (a.out_hi) {
+                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+                        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                        const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
+                        const size_t off = ((size_t)d.n * HW + y * W + x) * C + c0;
+                        *reinterpret_cast<uint2 *>(a.out_hi + off) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                        *reinterpret_cast<uint2 *>(a.out_lo + off) = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+                    } else {
+                        const float ov[4] = {o.x, o.y, o.z, o.w};
+                        float *ob = a.out + (int64_t)d.n * a.out_stride[0] + (int64_t)y * a.out_stride[2] + (int64_t)x * a.out_stride[3];
+                        const float *rb = a.feat_ref + (int64_t)d.n * a.ref_stride[0] + (int64_t)y * a.ref_stride[2] + (int64_t)x * a.ref_stride[3];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            float val = ov[e];
+                            if (a.add_ref) val += __ldg(rb + (int64_t)(c0 + e) * a.ref_stride[1]);
+                            ob[(int64_t)(c0 + e) * a.out_stride[1]] = val;
                         }
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ct.o_empty[j & 1]);
         };
 
+        const bool pt_on = tid == 0; (void)pt_on;
+        PT_DECL;
         int j = 0;
         for (;; j++) {
             named_bar(1, NT_WORK);                        // everyone is done with item j-1's table and item j-2's epilogue
+            PT(0);
             if (tid == 0 && j >= 2) mbar_arrive(&ct.desc_free[(j - 2) % NDESC]);
             wait_n(&ct.desc_full[j % NDESC], (uint32_t)(j / NDESC));
             const Desc &d = desc_at(j);
+            PT(1);
             if (d.tile < 0) break;
-            const int D = d.D, n = d.n, g0 = d.g0, gn = d.gn;
+            const int D = d.D, n = d.n;
             const int nch = (D + CHUNK - 1) / CHUNK;
 
-            // ---------------- B1: scores TMEM -> table[i][rank] ----------------
+            // ---------------- B1: scores TMEM -> T[rank][pixel] ----------------
             wait_n(&ct.s_full[j & 1], (uint32_t)(j >> 1));
             tc_fence_after();
+            PT(2);
             {
                 const int c = warp >> 2;
                 if (c < nch) {
@@ -249,148 +277,154 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     const int r = c * CHUNK + (warp & 3) * 32 + lane;
                     if (r < D) {
 #pragma unroll
-                        for (int i = 0; i < P; i++) table[i * DMAX + r] = v[i] + v2[i];
+                        for (int i = 0; i < P; i++) table[r * TP + i] = v[i] + v2[i];
                     }
                 }
             }
             tc_fence_before();
             named_bar(1, NT_WORK);
             if (tid == 0) mbar_arrive(&ct.s_empty[j & 1]);
+            PT(3);
 
-            // ---------------- B2: interpolate scores, softmax over K, outputs, β scatter ----------------
-            auto rank_of = [&](int pix) { return (int)d.prefix[pix >> 5] + __popc(d.bitmap[pix >> 5] & ((1u << (pix & 31)) - 1u)); };
-            {
-                constexpr int PW = P / NWORK;                          // 2 pixels per warp, interleaved for ILP; lane <-> sample
-                float x[PW][KPL], gxs[PW][KPL], gys[PW][KPL], tw[PW][KPL][4];
-                uint32_t rk[PW][KPL][2];
-                bool act[PW];
-                float mx[PW];
-                int py[PW], px[PW];
+            // ---------------- B2a: bilinear interpolation of the scores, ==0 mask, scale ----------------
+            const int i = lane;
+            const uint32_t p = d.pix[i];
+            const bool act = i >= d.g0 && i < d.g0 + d.gn && p != 0xFFFFFFFFu;
+            const int py = (int)(p >> 16), px = (int)(p & 0xffffu);
+            const int pofs = act ? py * W + px : 0;
+            const float4 en = d.ends[i];
+            float x[KW], tw[KW][4];
+            uint32_t rk[KW][2];
+            float mloc = -INFINITY;
 #pragma unroll
-                for (int u = 0; u < PW; u++) {
-                    const int i = warp + u * NWORK;
-                    const uint32_t p = d.pix[i];
-                    act[u] = i >= g0 && i < g0 + gn && p != 0xFFFFFFFFu;
-                    py[u] = (int)(p >> 16); px[u] = (int)(p & 0xffffu);
-                    mx[u] = -INFINITY;
+            for (int jj = 0; jj < KW; jj++) {
+                const int k = warp + NWORK * jj;
+                x[jj] = -INFINITY; rk[jj][0] = rk[jj][1] = 0u;
 #pragma unroll
-                    for (int jj = 0; jj < KPL; jj++) {
-                        const int k = jj * 32 + lane;
-                        x[u][jj] = -INFINITY; gxs[u][jj] = 0.f; gys[u][jj] = 0.f; rk[u][jj][0] = rk[u][jj][1] = 0u;
-#pragma unroll
-                        for (int tp = 0; tp < 4; tp++) tw[u][jj][tp] = 0.f;
-                        if (act[u] && k < K) {
-                            float gx, gy;
-                            sample_loc(d, i, k, gx, gy);
-                            gxs[u][jj] = gx; gys[u][jj] = gy;
-                            if (a.locs_out)
-                                reinterpret_cast<float2 *>(a.locs_out)[((size_t)k * a.N + n) * HW + py[u] * W + px[u]] = make_float2(gx, gy);
-                            const Taps t = make_taps(gx, gy, H, W, gc.align);
-                            float sim = 0.f;
-                            if (t.any) {
-                                uint32_t r[4] = {0u, 0u, 0u, 0u};
-#pragma unroll
-                                for (int tp = 0; tp < 4; tp++)
-                                    if (t.w[tp] != 0.f) {
-                                        r[tp] = (uint32_t)rank_of((t.y0 + (tp >> 1)) * W + t.x0 + (tp & 1));
-                                        tw[u][jj][tp] = t.w[tp];
-                                        sim = fmaf(t.w[tp], table[i * DMAX + r[tp]], sim);
-                                    }
-                                rk[u][jj][0] = r[0] | (r[1] << 16); rk[u][jj][1] = r[2] | (r[3] << 16);
-                            }
-                            if (sim == 0.f) sim = kMasked;                      // epipolar.py:298
-                            x[u][jj] = sim * sl2;
-                            mx[u] = fmaxf(mx[u], x[u][jj]);
-                        }
+                for (int tp = 0; tp < 4; tp++) tw[jj][tp] = 0.f;
+                if (act && k < K) {
+                    float gx, gy;
+                    if (a.locs_in) {
+                        const float2 l = __ldg(reinterpret_cast<const float2 *>(a.locs_in) + ((size_t)k * a.N + n) * HW + pofs);
+                        gx = l.x; gy = l.y;
+                    } else {
+                        gx = img2grid_x(lerp_exact(en.x, en.z, tkw[jj]), gc);
+                        gy = img2grid_y(lerp_exact(en.y, en.w, tkw[jj]), gc);
                     }
+                    if (a.locs_out) reinterpret_cast<float2 *>(a.locs_out)[((size_t)k * a.N + n) * HW + pofs] = make_float2(gx, gy);
+                    float sim = 0.f;
+                    const float ix = grid2pix(gx, W, gc.align), iy = grid2pix(gy, H, gc.align);
+                    if (D > 0 && ix > -1.f && ix < (float)W && iy > -1.f && iy < (float)H) {       // else: no tap in bounds (or NaN)
+                        const float fx = floorf(ix), fy = floorf(iy);
+                        const int x0 = (int)fx, y0 = (int)fy;
+                        const float ax = ix - fx, ay = iy - fy;
+                        const bool xin0 = x0 >= 0, xin1 = x0 + 1 < W, yin0 = y0 >= 0, yin1 = y0 + 1 < H;
+                        const float w00 = (xin0 && yin0) ? (1.f - ax) * (1.f - ay) : 0.f, w01 = (xin1 && yin0) ? ax * (1.f - ay) : 0.f;
+                        const float w10 = (xin0 && yin1) ? (1.f - ax) * ay : 0.f, w11 = (xin1 && yin1) ? ax * ay : 0.f;
+                        // ranks: one bitmap lookup per footprint row (the row's second pixel is marked too, so it is rank + 1)
+                        auto rank_of = [&](int pix) { return (int)d.prefix[pix >> 5] + __popc(d.bitmap[pix >> 5] & ((1u << (pix & 31)) - 1u)); };
+                        const int p00 = y0 * W + x0;
+                        int r00 = 0, r01 = 0, r10 = 0, r11 = 0;
+                        if (yin0) { if (xin0) { r00 = rank_of(p00); r01 = r00 + 1; } else r01 = rank_of(p00 + 1); }
+                        if (yin1) { if (xin0) { r10 = rank_of(p00 + W); r11 = r10 + 1; } else r11 = rank_of(p00 + W + 1); }
+                        const int rmax = D - 1;                      // defensive: a rank can never leave the table
+                        r00 = min(r00, rmax); r01 = min(r01, rmax); r10 = min(r10, rmax); r11 = min(r11, rmax);
+                        sim = w00 * table[r00 * TP + i];
+                        sim = fmaf(w01, table[r01 * TP + i], sim);
+                        sim = fmaf(w10, table[r10 * TP + i], sim);
+                        sim = fmaf(w11, table[r11 * TP + i], sim);
+                        tw[jj][0] = w00; tw[jj][1] = w01; tw[jj][2] = w10; tw[jj][3] = w11;
+                        rk[jj][0] = (uint32_t)r00 | ((uint32_t)r01 << 16); rk[jj][1] = (uint32_t)r10 | ((uint32_t)r11 << 16);
+                    }
+                    if (sim == 0.f) sim = kMasked;                      // epipolar.py:298
+                    x[jj] = sim * sl2;
+                    mloc = fmaxf(mloc, x[jj]);
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                    for (int u = 0; u < PW; u++) mx[u] = fmaxf(mx[u], __shfl_xor_sync(0xffffffffu, mx[u], o));
-                float sum[PW];
-#pragma unroll
-                for (int u = 0; u < PW; u++) {
-                    sum[u] = 0.f;
-#pragma unroll
-                    for (int jj = 0; jj < KPL; jj++) { x[u][jj] = (act[u] && jj * 32 + lane < K) ? exp2f(x[u][jj] - mx[u]) : 0.f; sum[u] += x[u][jj]; }
-                }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                    for (int u = 0; u < PW; u++) sum[u] += __shfl_xor_sync(0xffffffffu, sum[u], o);
-#pragma unroll
-                for (int u = 0; u < PW; u++) {
-                    if (!act[u]) continue;                              // warp-uniform
-                    const int i = warp + u * NWORK;
-                    const float inv = 1.f / sum[u];
-                    float best_v = -1.f, best_gx = 0.f, best_gy = 0.f;
-                    int best_k = 0x7fffffff;
-                    float *ab = a.attn ? a.attn + (size_t)n * K * HW + py[u] * W + px[u] : nullptr;
-#pragma unroll
-                    for (int jj = 0; jj < KPL; jj++) {
-                        const int k = jj * 32 + lane;
-                        x[u][jj] *= inv;
-                        if (k < K) {
-                            if (ab) ab[(size_t)k * HW] = x[u][jj];
-                            if (x[u][jj] > best_v) { best_v = x[u][jj]; best_k = k; best_gx = gxs[u][jj]; best_gy = gys[u][jj]; }
-                        }
-                    }
-                    if (a.corr_pos) {                                   // first maximum, like torch.argmax
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-                            const float ov = __shfl_xor_sync(0xffffffffu, best_v, o);
-                            const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
-                            const float ogx = __shfl_xor_sync(0xffffffffu, best_gx, o), ogy = __shfl_xor_sync(0xffffffffu, best_gy, o);
-                            if (ov > best_v || (ov == best_v && ok < best_k)) { best_v = ov; best_k = ok; best_gx = ogx; best_gy = ogy; }
-                        }
-                        if (lane == 0)
-                            reinterpret_cast<float2 *>(a.corr_pos)[(size_t)n * HW + py[u] * W + px[u]] =
-                                make_float2(grid2corr(best_gx, W, gc.correct), grid2corr(best_gy, H, gc.correct));
-                    }
-                    // β row: zero, then deterministic fixed-point scatter of a_k·w_kt
-                    int *trow = reinterpret_cast<int *>(table + i * DMAX);
-                    __syncwarp();
-                    for (int r = lane; r < D; r += 32) trow[r] = 0;
-                    __syncwarp();
-#pragma unroll
-                    for (int jj = 0; jj < KPL; jj++) {
-                        if (jj * 32 + lane < K) {
-#pragma unroll
-                            for (int tp = 0; tp < 4; tp++)
-                                if (tw[u][jj][tp] != 0.f) {
-                                    const uint32_t r = (rk[u][jj][tp >> 1] >> ((tp & 1) * 16)) & 0xffffu;
-                                    atomicAdd(&trow[r], __float2int_rn(x[u][jj] * tw[u][jj][tp] * FIX));
-                                }
-                        }
-                    }
-                }
-                __syncwarp();
-
-                // ---------------- β rows of this warp's pixels -> bf16 (hi, lo) stacked K-major panels ----------------
-                if (j >= 1) wait_n(&ct.o_full[(j - 1) & 1], (uint32_t)((j - 1) >> 1));   // GEMM2(j-1) has consumed the β panels
-#pragma unroll
-                for (int u = 0; u < PW; u++) {
-                    const int i = warp + u * NWORK;
-                    const int *trow = reinterpret_cast<const int *>(table + i * DMAX);
-                    float f[8];
-#pragma unroll
-                    for (int e = 0; e < 8; e++) {
-                        const int r = lane * 8 + e;
-                        f[e] = (act[u] && r < D) ? (float)trow[r] * (1.0f / FIX) : 0.f;
-                    }
-                    uint4 hi, lo;
-                    split8(f, hi, lo);
-                    const uint32_t off = (uint32_t)(lane >> 3) * PANEL_B2 + (uint32_t)i * 128u + (uint32_t)(((lane & 7) ^ (i & 7)) << 4);
-                    *reinterpret_cast<uint4 *>(bb + off) = hi;
-                    *reinterpret_cast<uint4 *>(bb + 4096 + off) = lo;
-                }
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&ct.beta_full);
             }
+            red_max[warp * 32 + lane] = mloc;
+            named_bar(1, NT_WORK);
+            PT(4);
+
+            // ---------------- B2b: softmax over K (16-way split), zero the table for the β scatter ----------------
+            float M = -INFINITY;
+#pragma unroll
+            for (int w = 0; w < NWORK; w++) M = fmaxf(M, red_max[w * 32 + lane]);
+            float sloc = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < KW; jj++) { x[jj] = (act && warp + NWORK * jj < K) ? exp2f(x[jj] - M) : 0.f; sloc += x[jj]; }
+            red_sum[warp * 32 + lane] = sloc;
+            for (int q = tid; q < D * TP; q += NT_WORK) Ti[q] = 0;
+            named_bar(1, NT_WORK);
+            float S = 0.f;
+#pragma unroll
+            for (int w = 0; w < NWORK; w++) S += red_sum[w * 32 + lane];
+            const float inv = 1.f / S;
+            float best_v = -1.f;
+            int best_k = 0x7fffffff;
+            float *ab = a.attn ? a.attn + (size_t)n * K * HW + pofs : nullptr;
+#pragma unroll
+            for (int jj = 0; jj < KW; jj++) {
+                const int k = warp + NWORK * jj;
+                if (act && k < K) {
+                    const float av = x[jj] * inv;
+                    if (ab) ab[(size_t)k * HW] = av;
+                    if (av > best_v) { best_v = av; best_k = k; }
+                    // deterministic fixed-point scatter of a_k·w_kt into β[rank][pixel]
+#pragma unroll
+                    for (int tp = 0; tp < 4; tp++)
+                        if (tw[jj][tp] != 0.f) {
+                            const uint32_t r = (rk[jj][tp >> 1] >> ((tp & 1) * 16)) & 0xffffu;
+                            atomicAdd(&Ti[r * TP + i], __float2int_rn(av * tw[jj][tp] * FIX));
+                        }
+                }
+            }
+            if (a.corr_pos) { red_bv[warp * 32 + lane] = best_v; red_bk[warp * 32 + lane] = best_k; }
+            named_bar(1, NT_WORK);
+            PT(5);
+            // ---------------- arg-max -> corr_pos (first maximum, like torch.argmax) ----------------
+            if (a.corr_pos && warp == 0 && act) {
+                float bv = -1.f; int bk = 0x7fffffff;
+#pragma unroll
+                for (int w = 0; w < NWORK; w++) {
+                    const float v = red_bv[w * 32 + lane]; const int kk = red_bk[w * 32 + lane];
+                    if (v > bv || (v == bv && kk < bk)) { bv = v; bk = kk; }
+                }
+                float gx, gy;
+                if (a.locs_in) {
+                    const float2 l = __ldg(reinterpret_cast<const float2 *>(a.locs_in) + ((size_t)bk * a.N + n) * HW + pofs);
+                    gx = l.x; gy = l.y;
+                } else {
+                    const float t = (float)bk / (float)(K - 1);
+                    gx = img2grid_x(lerp_exact(en.x, en.z, t), gc); gy = img2grid_y(lerp_exact(en.y, en.w, t), gc);
+                }
+                reinterpret_cast<float2 *>(a.corr_pos)[(size_t)n * HW + pofs] = make_float2(grid2corr(gx, W, gc.correct), grid2corr(gy, H, gc.correct));
+            }
+            // ---------------- β[rank][pixel] -> bf16 (hi, lo) stacked K-major panels; warp <-> 16 ranks, lane <-> pixel ----------------
+            if (j >= 1) wait_n(&ct.o_full[(j - 1) & 1], (uint32_t)((j - 1) >> 1));   // GEMM2(j-1) has consumed the β panels
+            PT(6);
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const int d0 = warp * 16 + hh * 8;
+                float f[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) f[e] = (act && d0 + e < D) ? (float)Ti[(d0 + e) * TP + i] * (1.0f / FIX) : 0.f;
+                uint4 hi, lo;
+                split8(f, hi, lo);
+                const uint32_t off = (uint32_t)(d0 >> 6) * PANEL_B2 + (uint32_t)i * 128u + (uint32_t)((((d0 & 63) >> 3) ^ (i & 7)) << 4);
+                *reinterpret_cast<uint4 *>(bb + off) = hi;
+                *reinterpret_cast<uint4 *>(bb + 4096 + off) = lo;
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ct.beta_full);
+            named_bar(1, NT_WORK);                          // the table is free: the epilogue transposes through it
+            PT(7);
             // ---------------- epilogue of the previous item (its GEMM2 ran during this item's softmax) ----------------
             if (j >= 1) { tc_fence_after(); epilogue(j - 1); }
+            PT(9);
+#ifdef EPI_PIPE_TIMERS
+            if (pt_on) atomicAdd(&g_pipe_timers[8], 1ull);
+#endif
         }
         if (j >= 1) {                                   // drain
             wait_n(&ct.o_full[(j - 1) & 1], (uint32_t)((j - 1) >> 1));
@@ -399,14 +433,37 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
         }
     } else if (warp < W_GATHER) {
         // =====================================================================================================
-        // SETUP (2 warps): build work items
+        // SETUP (4 warps): build work items
         // =====================================================================================================
-        const int st = tid - W_SETUP * 32;                 // 0..63
+        const int st = tid - W_SETUP * 32;                 // 0..127
         const int sw = warp - W_SETUP;
         int claimed = 0;
+        const bool pt_on = st == 0; (void)pt_on;
+        PT_DECL;
+        float tk[KPL];                                      // this lane's sample parameters k/(K-1), k = lane + 32 jj
+#pragma unroll
+        for (int jj = 0; jj < KPL; jj++) tk[jj] = (float)(lane + 32 * jj) / (float)(K - 1);
+        // every in-bounds pixel of the 2x2 bilinear footprint (a superset of the taps with non-zero weight)
+        auto mark = [&](Desc &d, float gx, float gy) {
+            const float ix = grid2pix(gx, W, gc.align), iy = grid2pix(gy, H, gc.align);
+            if (!(ix > -1.f && ix < (float)W && iy > -1.f && iy < (float)H)) return;       // also rejects NaN / far sentinels
+            const int x0 = (int)floorf(ix), y0 = (int)floorf(iy);                          // -1 .. size-1
+            const bool xin0 = x0 >= 0, xin1 = x0 + 1 < W, yin0 = y0 >= 0, yin1 = y0 + 1 < H;
+            const int p00 = y0 * W + x0;
+            if (yin0) {
+                if (xin0) atomicOr(&d.bitmap[p00 >> 5], 1u << (p00 & 31));
+                if (xin1) atomicOr(&d.bitmap[(p00 + 1) >> 5], 1u << ((p00 + 1) & 31));
+            }
+            if (yin1) {
+                const int p10 = p00 + W;
+                if (xin0) atomicOr(&d.bitmap[p10 >> 5], 1u << (p10 & 31));
+                if (xin1) atomicOr(&d.bitmap[(p10 + 1) >> 5], 1u << ((p10 + 1) & 31));
+            }
+        };
         for (int j = 0;; j++) {
             Desc &d = desc_at(j);
             if (j >= NDESC) wait_n(&ct.desc_free[j % NDESC], (uint32_t)(j / NDESC - 1));
+            PT(10);
             bool done = false;
             while (true) {
                 // ---- next group: pop the split stack or claim a new tile ----
@@ -421,47 +478,52 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     }
                     if (!ct.done) ct.cur = ct.stack[--ct.sp];
                 }
-                named_bar(2, 64);
+                named_bar(2, NSETUP);
                 if (ct.done) { done = true; break; }
                 const int tile = ct.cur_tile, g0 = ct.cur & 0xff, gn = ct.cur >> 8;
                 const int n = tile / tiles_per_item, trem = tile % tiles_per_item;
-                if (st < P) {
+                if (st < P) {                               // pixel + its epipolar line end points
                     const int e = trem * P + st;
-                    unsigned p = 0xFFFFu;
+                    unsigned p = 0u;
                     if (e < HW) p = a.order ? (unsigned)a.order[(size_t)n * HW + e] : (unsigned)e;
-                    d.pix[st] = (e < HW) ? ((uint32_t)(p / W) << 16 | (uint32_t)(p % W)) : 0xFFFFFFFFu;
-                }
-                if (st == 32) { d.tile = tile; d.n = n; d.g0 = g0; d.gn = gn; }
-                if (st == 33 && !a.locs_in) d.geom = a.pair_geom[n];
-                for (int w = st; w < nwords; w += 64) d.bitmap[w] = 0u;
-                named_bar(2, 64);
-                if (st < P) {
-                    float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
-                    const uint32_t p = d.pix[st];
-                    if (p != 0xFFFFFFFFu && !a.locs_in)
-                        line_endpoints(d.geom, gc, pix2coord((int)(p & 0xffffu), gc.ds, gc.r), pix2coord((int)(p >> 16), gc.ds, gc.r), e.x, e.y, e.z, e.w);
-                    d.ends[st] = e;
-                }
-                named_bar(2, 64);
-                // ---- union of the in-bounds taps: lane <-> sample (consecutive samples fall into different words) ----
-                for (int i = g0 + sw; i < g0 + gn; i += 2) {
-                    if (d.pix[i] == 0xFFFFFFFFu) continue;
-                    for (int k = lane; k < K; k += 32) {
-                        float gx, gy;
-                        sample_loc(d, i, k, gx, gy);
-                        const Taps t = make_taps(gx, gy, H, W, gc.align);
-                        if (t.any) {
+                    const int py = (int)(p / W), px = (int)(p % W);
+                    d.pix[st] = (e < HW) ? ((uint32_t)py << 16 | (uint32_t)px) : 0xFFFFFFFFu;
+                    float4 en = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (e < HW && !a.locs_in) {
+                        PairGeom g;
+                        const float *gp = reinterpret_cast<const float *>(a.pair_geom + n);
 #pragma unroll
-                            for (int tp = 0; tp < 4; tp++)
-                                if (t.w[tp] != 0.f) {
-                                    const int pix = (t.y0 + (tp >> 1)) * W + t.x0 + (tp & 1);
-                                    atomicOr(&d.bitmap[pix >> 5], 1u << (pix & 31));
-                                }
+                        for (int q = 0; q < 9; q++) g.M[q] = __ldg(gp + q);
+                        g.ex = __ldg(gp + 9); g.ey = __ldg(gp + 10);
+                        line_endpoints(g, gc, pix2coord(px, gc.ds, gc.r), pix2coord(py, gc.ds, gc.r), en.x, en.y, en.z, en.w);
+                    }
+                    d.ends[st] = en;
+                } else if (st == P) { d.tile = tile; d.n = n; d.g0 = g0; d.gn = gn; }
+                for (int w = st - 64; w >= 0 && w < nwords; w += 64) d.bitmap[w] = 0u;     // warps 2,3 clear the bitmap
+                named_bar(2, NSETUP);
+                // ---- union of the in-bounds taps: lane <-> sample (consecutive samples fall into different words) ----
+                for (int i = g0 + sw; i < g0 + gn; i += NSETUP / 32) {
+                    const uint32_t p = d.pix[i];
+                    if (p == 0xFFFFFFFFu) continue;
+                    if (a.locs_in) {
+#pragma unroll
+                        for (int jj = 0; jj < KPL; jj++) {
+                            const int k = lane + 32 * jj;
+                            if (k < K) {
+                                const float2 l = __ldg(reinterpret_cast<const float2 *>(a.locs_in) + ((size_t)k * a.N + n) * HW + (p >> 16) * W + (p & 0xffffu));
+                                mark(d, l.x, l.y);
+                            }
                         }
+                    } else {
+                        const float4 e = d.ends[i];
+#pragma unroll
+                        for (int jj = 0; jj < KPL; jj++)
+                            if (lane + 32 * jj < K)
+                                mark(d, img2grid_x(lerp_exact(e.x, e.z, tk[jj]), gc), img2grid_y(lerp_exact(e.y, e.w, tk[jj]), gc));
                     }
                 }
-                named_bar(2, 64);
-                // ---- exclusive prefix of popcounts (warp 0 of the pair; 16 words per lane max) ----
+                named_bar(2, NSETUP);
+                // ---- exclusive prefix of popcounts (first setup warp; 16 words per lane max) ----
                 if (sw == 0) {
                     const int per = (nwords + 31) >> 5;
                     int cnt = 0;
@@ -476,7 +538,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     }
                     if (lane == 31) ct.total = incl;
                 }
-                named_bar(2, 64);
+                named_bar(2, NSETUP);
                 const int D = ct.total;
                 if (D > DMAX && gn > 1) {                 // split the group
                     if (st == 0) {
@@ -484,22 +546,22 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                         ct.stack[ct.sp++] = (g0 + h1) | ((gn - h1) << 8);
                         ct.stack[ct.sp++] = g0 | (h1 << 8);
                     }
-                    named_bar(2, 64);
+                    named_bar(2, NSETUP);
                     continue;
                 }
                 const int Dc = D > DMAX ? 0 : D;          // a single pixel over DMAX cannot happen for supported shapes (host check)
                 if (D > DMAX && st == 0 && a.err_flag) atomicOr(a.err_flag, 1);
                 // ---- union list: idx[rank] = source pixel; pad to a multiple of 16 with a valid row ----
                 if (Dc > 0)
-                    for (int w = st; w < nwords; w += 64) {
+                    for (int w = st; w < nwords; w += NSETUP) {
                         uint32_t bits = d.bitmap[w];
                         int r = d.prefix[w];
                         while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; d.idx[r++] = (uint16_t)(w * 32 + b); }
                     }
-                named_bar(2, 64);
+                named_bar(2, NSETUP);
                 if (st < 16 && Dc > 0) { const int r = Dc + st; if (r < ((Dc + 15) & ~15)) d.idx[r] = d.idx[0]; }
                 if (st == 16) d.D = Dc;
-                named_bar(2, 64);
+                named_bar(2, NSETUP);
                 break;
             }
             if (done) {
@@ -507,6 +569,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 break;
             }
             if (st == 0) mbar_arrive(&ct.desc_full[j % NDESC]);
+            PT(11);
         }
     } else if (warp < W_MMA) {
         // =====================================================================================================
@@ -518,9 +581,13 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
         const __nv_bfloat16 *planes = a.ref_hi;          // [ref_hi | ref_lo | src_hi | src_lo], each [N*HW][C]
         const size_t plane_elems = (size_t)NHW * C;
         uint32_t qcount = 0, fcount = 0;
+        const bool pt_on = gt == 0; (void)pt_on;
+        PT_DECL;
         auto stage_acquire = [&]() -> uint8_t * {
             const uint32_t s = fcount % NSTAGE;
+            PT(13);
             if (fcount >= NSTAGE) wait_n(&ct.f_empty[s], fcount / NSTAGE - 1);
+            PT(14);
             return smem + OFF_STAGE + s * STAGE_BYTES;
         };
         auto arrive_async = [&](uint64_t *bar) {
@@ -555,12 +622,15 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 }
         };
         for (int j = 0;; j++) {
+            PT(13);
             wait_n(&ct.desc_full[j % NDESC], (uint32_t)(j / NDESC));
+            PT(15);
             const Desc &d = desc_at(j);
             const bool last = d.tile < 0;
             if (!last && d.D > 0) {
                 // ---- query rows of the item's pixels: stacked panels [hi 32 rows | lo 32 rows] x NP ----
                 if (qcount >= 1) wait_n(&ct.q_empty, qcount - 1);
+                PT(16);
                 {
                     const __nv_bfloat16 *ref = planes + (size_t)d.n * HW * C;
 #pragma unroll
@@ -619,10 +689,15 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
         // =====================================================================================================
         uint32_t qcount = 0, fcount = 0;
         const uint32_t sq = smem_u32(smem + OFF_Q), sb = smem_u32(smem + OFF_BETA);
+        const bool pt_on = lane == 0; (void)pt_on;
+        PT_DECL;
         auto gemm2 = [&](int jj) {
             const Desc &d = desc_at(jj);
+            PT(20);
             wait_n(&ct.beta_full, (uint32_t)jj);
+            PT(21);
             if (jj >= 2) wait_n(&ct.o_empty[jj & 1], (uint32_t)((jj >> 1) - 1));
+            PT(22);
             tc_fence_after();
             if (d.D > 0) {
                 const int D16 = (d.D + 15) & ~15, nblk = (D16 + 63) >> 6;
@@ -630,7 +705,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 for (int h = 0; h < NH; h++)
                     for (int blk = 0; blk < nblk; blk++) {
                         const uint32_t s = fcount % NSTAGE;
+                        PT(20);
                         wait_n(&ct.f_full[s], fcount / NSTAGE);
+                        PT(23);
                         fence_proxy_async_smem();           // cp.async (generic proxy) writes -> tcgen05.mma (async proxy) reads
                         tc_fence_after();
                         if (lane == 0) {
@@ -653,21 +730,27 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
             __syncwarp();
         };
         for (int j = 0;; j++) {
+            PT(20);
             wait_n(&ct.desc_full[j % NDESC], (uint32_t)(j / NDESC));
+            PT(24);
             const Desc &d = desc_at(j);
             const bool last = d.tile < 0;
             if (!last) {
                 if (j >= 2) wait_n(&ct.s_empty[j & 1], (uint32_t)((j >> 1) - 1));
+                PT(25);
                 tc_fence_after();
                 if (d.D > 0) {
                     wait_n(&ct.q_full, qcount);
+                    PT(26);
                     fence_proxy_async_smem();
                     const int nch = (d.D + CHUNK - 1) / CHUNK;
                     const uint32_t idesc64 = make_idesc_bf16(128, 2 * P, 0, 0), idesc32 = make_idesc_bf16(128, P, 0, 0);
                     for (int c = 0; c < nch; c++)
                         for (int kp = 0; kp < NP; kp++) {
                             const uint32_t s = fcount % NSTAGE;
+                            PT(20);
                             wait_n(&ct.f_full[s], fcount / NSTAGE);
+                            PT(27);
                             fence_proxy_async_smem();
                             tc_fence_after();
                             if (lane == 0) {
@@ -702,6 +785,13 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
     if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+
+#ifdef EPI_PIPE_TIMERS
+extern "C" void epi_pipe_timers_read(unsigned long long *out32, int reset) {
+    cudaMemcpyFromSymbol(out32, g_pipe_timers, sizeof(unsigned long long) * 32);
+    if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_pipe_timers, z, sizeof(z)); }
+}
+#endif
 
 bool fusion_pipe_shape_ok(int C, int H, int W, int K, bool has_locs_in) {
     if (C % 8 != 0 || C > 256 || C < 8) return false;

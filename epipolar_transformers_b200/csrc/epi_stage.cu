@@ -37,6 +37,14 @@ __device__ __forceinline__ float angle_key(int i, int W, const GeomCfg &gc, floa
 }
 }  // namespace stg
 
+#ifdef EPI_PIPE_TIMERS
+__device__ unsigned long long g_stage_timers[16];
+#define ST(slot) do { __syncthreads(); if (t == 0 && blockIdx.x == 0) { const long long t_ = clock64(); g_stage_timers[slot] = (unsigned long long)(t_ - st_prev); st_prev = t_; } } while (0)
+extern "C" void epi_stage_timers_read(unsigned long long *out16) { cudaMemcpyFromSymbol(out16, g_stage_timers, sizeof(unsigned long long) * 16); }
+#else
+#define ST(slot) do { } while (0)
+#endif
+
 struct StageArgs {
     const float *ref, *src;
     int64_t ref_stride[4], src_stride[4];
@@ -66,6 +74,9 @@ __global__ void __launch_bounds__(stg::NT) epi_stage_kernel(const StageArgs s) {
         __shared__ float s_e[4];
         __shared__ int s_warp[NT / 32];
         __shared__ int s_big[64], s_nbig;
+#ifdef EPI_PIPE_TIMERS
+        long long st_prev = clock64();
+#endif
         const int n = blockIdx.x;
         if (t == 0) {
             const float *P1 = s.P_ref + 12 * n, *P2 = s.P_src + 12 * n;
@@ -96,11 +107,13 @@ __global__ void __launch_bounds__(stg::NT) epi_stage_kernel(const StageArgs s) {
         }
         for (int b = t; b < NBIN; b += NT) hist[b] = 0;
         __syncthreads();
+        ST(0);
         const float ex = s_e[0], ey = s_e[1], a0 = s_e[2];
         const bool parallel = s_e[3] != 0.f;
         const float span = fabsf(s.gc.xmax - s.gc.xmin) + fabsf(s.gc.ymax - s.gc.ymin) + 1.f;
         for (int i = t; i < HW; i += NT) atomicAdd(&hist[(int)(angle_key(i, W, s.gc, ex, ey, a0, parallel, span) * (float)NBIN)], 1);
         __syncthreads();
+        ST(1);
         // exclusive scan over the bins: 16 consecutive bins per thread, then a block scan of the partial sums
         constexpr int PER = NBIN / NT;
         int loc[PER], sum = 0;
@@ -118,6 +131,7 @@ __global__ void __launch_bounds__(stg::NT) epi_stage_kernel(const StageArgs s) {
 #pragma unroll
         for (int q = 0; q < PER; q++) { hist[t * PER + q] = base; base += loc[q]; }
         __syncthreads();
+        ST(2);
         // placement (arbitrary order inside a bin) into the scratch list
         uint16_t *tmp = s.order_tmp + (size_t)n * HW, *ord = s.order + (size_t)n * HW;
         for (int i = t; i < HW; i += NT) {
@@ -125,6 +139,7 @@ __global__ void __launch_bounds__(stg::NT) epi_stage_kernel(const StageArgs s) {
             tmp[atomicAdd(&hist[b], 1)] = (uint16_t)i;
         }
         __syncthreads();
+        ST(3);
         // inside every bin: ascending pixel index (insertion sort; bins hold ~HW/4096 entries)
         {
             int st0 = start0;
@@ -148,6 +163,7 @@ __global__ void __launch_bounds__(stg::NT) epi_stage_kernel(const StageArgs s) {
             }
         }
         __syncthreads();
+        ST(4);
         // degenerate cameras only: big bins are ranked by counting, the whole block per bin
         const int nbig = s_nbig < 64 ? s_nbig : 64;
         for (int bb = 0; bb < nbig; bb++) {

@@ -1,0 +1,36 @@
+"""Developer tool: per-role cycle totals of the pipelined fused kernel (library built with
+`python -m epipolar_transformers_b200.build --timers`)."""
+import ctypes, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from epipolar_transformers_b200 import _lib
+_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libepipolar_b200_timers.so")
+import epipolar_transformers_b200 as epi
+from epipolar_transformers_b200 import synthetic as syn
+lib = _lib.load()
+N, C, K = 4, 256, 64
+H = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+W = H
+P1, P2 = syn.pairs_from_ring(N, 4 * H)
+f1 = torch.relu(torch.randn(N, C, H, W, device="cuda")); f2 = torch.relu(torch.randn(N, C, H, W, device="cuda"))
+P1 = torch.from_numpy(P1.astype(np.float32)).cuda(); P2 = torch.from_numpy(P2.astype(np.float32)).cuda()
+buf = (ctypes.c_ulonglong * 32)()
+for it in range(3):
+    epi.epipolar_fusion(f1, f2, P1, P2, K=K, correct_normalize=True, variant="pipe")
+    torch.cuda.synchronize()
+    lib.epi_pipe_timers_read(buf, 1)
+v = np.array(list(buf), dtype=np.float64)
+items = v[8]
+print("items %d (tiles %d)" % (items, N * ((H * W + 31) // 32)))
+names = {0: "W bar(top)", 1: "W wait desc", 2: "W wait S", 3: "W B1+bar", 4: "W B2a sims", 5: "W B2b softmax+scatter", 6: "W argmax+wait O(j-1)", 7: "W beta conv+bar", 9: "W epilogue",
+         10: "S wait desc_free", 11: "S build item", 13: "G issue/work", 14: "G wait f_empty", 15: "G wait desc", 16: "G wait q_empty",
+         20: "M issue/work", 21: "M wait beta", 22: "M wait o_empty", 23: "M wait f_full (G2)", 24: "M wait desc", 25: "M wait s_empty",
+         26: "M wait q_full", 27: "M wait f_full (G1)"}
+for k in sorted(names):
+    print("%-24s %9.0f cyc/item" % (names[k], v[k] / max(items, 1)))
+for lo, hi, nm in ((0, 8, "workers(excl epi)"), (10, 12, "setup"), (13, 17, "gather"), (20, 28, "mma")):
+    print("%-10s total %9.0f cyc/item" % (nm, v[lo:hi].sum() / max(items, 1)))
+
+sb = (ctypes.c_ulonglong * 16)()
+lib.epi_stage_timers_read(sb)
+print("stage order block (cycles): geom+zero %d, hist %d, scan %d, place %d, binsort %d" % tuple(list(sb)[:5]))
