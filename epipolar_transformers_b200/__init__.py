@@ -10,10 +10,10 @@ include/epipolar_b200.h).  Importing this package does not need a GPU; calling t
 and fails loudly if the library is missing.
 """
 from .config import Node, default_cfg, make_cfg, get_global_cfg, set_global_cfg, cfg_h36m_r50_256, cfg_h36m_r152_384
-from .epipolar import Epipolar, ZeroInitBN, epipolar_fusion, fold_z_bn, sample_locs, fused_other_feat
+from .epipolar import Epipolar, FusionState, ZeroInitBN, epipolar_fusion, fold_z_bn, sample_locs, fused_other_feat
 from .host_pipeline import HostStreamer
 from . import multiview, synthetic
 
-__all__ = ["Epipolar", "HostStreamer", "ZeroInitBN", "epipolar_fusion", "fold_z_bn", "sample_locs", "fused_other_feat",
+__all__ = ["Epipolar", "FusionState", "HostStreamer", "ZeroInitBN", "epipolar_fusion", "fold_z_bn", "sample_locs", "fused_other_feat",
            "Node", "default_cfg", "make_cfg", "get_global_cfg", "set_global_cfg",
            "cfg_h36m_r50_256", "cfg_h36m_r152_384", "multiview", "synthetic"]

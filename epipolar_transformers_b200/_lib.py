@@ -11,12 +11,12 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libepipolar_b200.so")
 
-EPI_ABI_VERSION = 1
+EPI_ABI_VERSION = 2
 EPI_VARIANT_AUTO, EPI_VARIANT_WARP, EPI_VARIANT_TILE, EPI_VARIANT_SECTOR, EPI_VARIANT_PIPE = 0, 1, 2, 3, 4
 VARIANTS = {"auto": EPI_VARIANT_AUTO, "warp": EPI_VARIANT_WARP, "tile": EPI_VARIANT_TILE, "sector": EPI_VARIANT_SECTOR,
             "pipe": EPI_VARIANT_PIPE}
 
-EXPORTS = ("epi_version", "epi_last_error", "epi_fusion_workspace_bytes", "epi_fusion_forward_f32",
+EXPORTS = ("epi_version", "epi_last_error", "epi_fusion_workspace_bytes", "epi_fusion_cache_bytes", "epi_fusion_forward_f32",
            "epi_sample_locs_f32", "epi_fold_z_bn_f32", "epi_last_launch_count", "epi_umma_selftest",
            "epi_kernel_timing_enable", "epi_kernel_timing_last_ms")
 
@@ -37,6 +37,7 @@ class EpiFusionParams(ctypes.Structure):
         ("downsample", ctypes.c_float), ("img_scale", ctypes.c_float), ("eps", ctypes.c_float), ("softmax_scale", ctypes.c_float),
         ("align_corners", ctypes.c_int32), ("correct_normalize", ctypes.c_int32), ("z_residual", ctypes.c_int32),
         ("add_ref_residual", ctypes.c_int32), ("variant", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3),
+        ("cache", ctypes.c_void_p), ("cache_bytes", ctypes.c_size_t),
     ]
 
 
@@ -61,6 +62,8 @@ def load():
     lib.epi_last_launch_count.restype = ctypes.c_int
     lib.epi_fusion_workspace_bytes.restype = ctypes.c_size_t
     lib.epi_fusion_workspace_bytes.argtypes = [ctypes.POINTER(EpiFusionParams)]
+    lib.epi_fusion_cache_bytes.restype = ctypes.c_size_t
+    lib.epi_fusion_cache_bytes.argtypes = [ctypes.POINTER(EpiFusionParams)]
     lib.epi_fusion_forward_f32.restype = ctypes.c_int
     lib.epi_fusion_forward_f32.argtypes = [ctypes.POINTER(EpiFusionParams), ctypes.c_void_p]
     lib.epi_sample_locs_f32.restype = ctypes.c_int

@@ -28,7 +28,7 @@ bool src_is_channels_last(const EpiFusionParams *p) {
 }
 
 struct Plan {
-    size_t off_src = 0, off_prez = 0, off_counter = 0, off_ref = 0, off_order = 0, off_order_tmp = 0, off_geom = 0, total = 0;
+    size_t off_src = 0, off_prez = 0, off_counter = 0, off_ref = 0, off_order = 0, off_wplanes = 0, off_geom = 0, total = 0;
     bool stage_src = false, has_z = false, tile = false, sector = false, pipe = false;
 };
 
@@ -54,9 +54,11 @@ Plan make_plan(const EpiFusionParams *p) {
         pl.off_ref = off; off += align_up(2 * map);
         if (pl.has_z) { pl.off_prez = off; off += align_up(map); }
         pl.off_counter = off; off += 256;
-        pl.off_order = off; off += align_up((size_t)p->N * p->H * p->W * sizeof(uint16_t));
-        pl.off_order_tmp = off; off += align_up((size_t)p->N * p->H * p->W * sizeof(uint16_t));
-        pl.off_geom = off; off += align_up((size_t)p->N * sizeof(epi::PairGeom));
+        if (pl.has_z && epi::zgemm_supported(p->C)) { pl.off_wplanes = off; off += align_up((size_t)p->C * p->C * 4); }
+        if (!p->cache) {               // no persistent cache: pixel order and pair constants are rebuilt in the workspace every call
+            pl.off_order = off; off += align_up((size_t)p->N * p->H * p->W * sizeof(uint16_t));
+            pl.off_geom = off; off += align_up((size_t)p->N * sizeof(epi::PairGeom));
+        }
         pl.total = off;
         return pl;
     }
@@ -126,6 +128,12 @@ float epi_kernel_timing_last_ms(void) {
     return ms;
 }
 
+size_t epi_fusion_cache_bytes(const EpiFusionParams *p) {
+    if (!p || p->N <= 0 || p->C <= 0 || p->H <= 0 || p->W <= 0 || !want_pipe(p)) return 0;
+    return align_up((size_t)p->N * 32 * sizeof(float)) + align_up((size_t)p->N * sizeof(epi::PairGeom)) +
+           align_up((size_t)p->N * p->H * p->W * sizeof(uint16_t));
+}
+
 size_t epi_fusion_workspace_bytes(const EpiFusionParams *p) {
     if (!p || p->N <= 0 || p->C <= 0 || p->H <= 0 || p->W <= 0) return 0;
     return make_plan(p).total;
@@ -141,6 +149,7 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
     char *ws = static_cast<char *>(p->workspace);
     int launches = 0;
     cudaError_t e;
+    const __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;
 
     epi::FusionArgs a;
     memset(&a, 0, sizeof(a));
@@ -157,12 +166,28 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
         __nv_bfloat16 *planes = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_ref);
         int *words = reinterpret_cast<int *>(ws + pl.off_counter);
         const bool have_P = p->P_ref && p->P_src;
-        uint16_t *order = have_P ? reinterpret_cast<uint16_t *>(ws + pl.off_order) : nullptr;
-        epi::PairGeom *pg = reinterpret_cast<epi::PairGeom *>(ws + pl.off_geom);
-        e = epi::launch_stage(p->feat_ref, p->ref_stride, p->feat_src, p->src_stride, planes, p->P_ref, p->P_src, pg, order,
-                              reinterpret_cast<uint16_t *>(ws + pl.off_order_tmp), words, p->N, p->C, p->H, p->W, a.geom, st);
+        uint16_t *order = nullptr;
+        epi::PairGeom *pg = nullptr;
+        float *okey = nullptr;
+        if (p->cache) {
+            if (p->cache_bytes < epi_fusion_cache_bytes(p)) return fail(EPI_EWORKSPACE, "cache too small");
+            if (reinterpret_cast<uintptr_t>(p->cache) % 256 != 0) return fail(EPI_EINVAL, "cache must be 256-byte aligned");
+            char *cb = static_cast<char *>(p->cache);
+            okey = reinterpret_cast<float *>(cb);
+            pg = reinterpret_cast<epi::PairGeom *>(cb + align_up((size_t)p->N * 32 * sizeof(float)));
+            order = reinterpret_cast<uint16_t *>(cb + align_up((size_t)p->N * 32 * sizeof(float)) + align_up((size_t)p->N * sizeof(epi::PairGeom)));
+        } else {
+            order = reinterpret_cast<uint16_t *>(ws + pl.off_order);
+            pg = reinterpret_cast<epi::PairGeom *>(ws + pl.off_geom);
+        }
+        if (!have_P) { order = nullptr; okey = nullptr; }
+        const bool z_planes = pl.has_z && epi::zgemm_supported(p->C);
+        __nv_bfloat16 *wpl = z_planes ? reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_wplanes) : nullptr;
+        e = epi::launch_stage(p->feat_ref, p->ref_stride, p->feat_src, p->src_stride, planes, p->P_ref, p->P_src, pg, order, okey,
+                              z_planes ? p->z_weight_folded : nullptr, wpl, words, p->N, p->C, p->H, p->W, a.geom, st);
         if (e != cudaSuccess) return fail(EPI_ECUDA, "operand staging launch failed: %s", cudaGetErrorString(e));
         launches++;
+        w_hi = wpl; w_lo = wpl ? wpl + (size_t)p->C * p->C : nullptr;
         a.ref_hi = planes; a.ref_lo = planes + elems; a.src_hi = planes + 2 * elems; a.src_lo = planes + 3 * elems;
         a.order = order; a.pair_geom = pg; a.tile_counter = words; a.err_flag = words + 1;
     } else
@@ -197,7 +222,7 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
         a.src_nhwc = p->feat_src;
     }
 
-    const bool z_tc = pl.has_z && (pl.tile || pl.pipe) && epi::zgemm_supported(p->C);
+    const bool z_tc = pl.has_z && pl.pipe && epi::zgemm_supported(p->C);      // tensor-core z GEMM (operand planes come from the staging launch)
     if (z_tc) {         // fused feature leaves the tile kernel as bf16 (hi, lo) planes: the A operand of the z GEMM
         a.out = nullptr;
         a.out_hi = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_prez);
@@ -229,7 +254,7 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
     if (z_tc) {
         epi::ZGemmArgs z;
         memset(&z, 0, sizeof(z));
-        z.x_hi = a.out_hi; z.x_lo = a.out_lo; z.Wf = p->z_weight_folded; z.bf = p->z_bias_folded;
+        z.x_hi = a.out_hi; z.x_lo = a.out_lo; z.w_hi = w_hi; z.w_lo = w_lo; z.Wf = p->z_weight_folded; z.bf = p->z_bias_folded;
         z.ref = p->feat_ref; z.y = p->out;
         for (int i = 0; i < 4; i++) { z.y_stride[i] = p->out_stride[i]; z.ref_stride[i] = p->ref_stride[i]; }
         z.N = p->N; z.C = p->C; z.HW = p->H * p->W; z.W = p->W; z.Npad = p->C;

@@ -41,7 +41,7 @@ constexpr int NT_ALL = 800;
 constexpr int MAXWORDS = 512;      // bitmap words: H*W <= 16384
 constexpr int MAXKPL = 4;          // samples per lane: K <= 128
 constexpr int NSTAGE = 3;
-constexpr int NDESC = 3;
+constexpr int NDESC = 4;
 constexpr float FIX = 1073741824.0f;           // 2^30 fixed point for the β scatter (bit-reproducible)
 
 constexpr uint32_t STAGE_BYTES = 32768;        // GEMM1: [plane][128 rows x 128 B]; GEMM2: [plane][2 panels][64 rows x 128 B]
@@ -50,9 +50,11 @@ constexpr uint32_t PANEL_B2 = 8192;            // stacked B panel: 64 rows x 128
 constexpr uint32_t OFF_STAGE = 0;
 constexpr uint32_t OFF_Q = NSTAGE * STAGE_BYTES;           // 4 stacked panels
 constexpr uint32_t OFF_BETA = OFF_Q + 4 * PANEL_B2;        // 4 stacked panels (256 d)
-constexpr int TP = 33;             // row pitch (floats) of the d-major score table T[rank][pixel]
-constexpr uint32_t OFF_TABLE = OFF_BETA + 4 * PANEL_B2;    // [DMAX][33] fp32 scores, then int32 β, then the epilogue's [32][256] transposition
-constexpr uint32_t OFF_RED = OFF_TABLE + DMAX * TP * 4;    // softmax / arg-max split-reduction scratch [4][16][32]
+// d-major score table T[rank][pixel]: 32 floats per row, the float4 column XOR-ed with rank % 8.  Lane <-> pixel accesses hit
+// bank (pixel-derived) regardless of each lane's rank pattern; lane <-> rank accesses (TMEM read-out) are conflict free too.
+__device__ __forceinline__ int tix(int r, int i) { return r * 32 + ((((i >> 2) ^ r) & 7) << 2) + (i & 3); }
+constexpr uint32_t OFF_TABLE = OFF_BETA + 4 * PANEL_B2;    // [DMAX][32] fp32 scores, then int32 β, then the epilogue's [32][256] transposition
+constexpr uint32_t OFF_RED = OFF_TABLE + DMAX * 32 * 4;    // softmax / arg-max split-reduction scratch [4][16][32]
 constexpr uint32_t OFF_DESC = OFF_RED + 4 * NWORK * 32 * 4;
 
 struct Desc {                      // one work item, written by the setup warps
@@ -277,7 +279,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     const int r = c * CHUNK + (warp & 3) * 32 + lane;
                     if (r < D) {
 #pragma unroll
-                        for (int i = 0; i < P; i++) table[r * TP + i] = v[i] + v2[i];
+                        for (int c4 = 0; c4 < 8; c4++)
+                            *reinterpret_cast<float4 *>(table + r * 32 + (((c4 ^ r) & 7) << 2)) =
+                                make_float4(v[4 * c4] + v2[4 * c4], v[4 * c4 + 1] + v2[4 * c4 + 1], v[4 * c4 + 2] + v2[4 * c4 + 2], v[4 * c4 + 3] + v2[4 * c4 + 3]);
                     }
                 }
             }
@@ -329,10 +333,10 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                         if (yin1) { if (xin0) { r10 = rank_of(p00 + W); r11 = r10 + 1; } else r11 = rank_of(p00 + W + 1); }
                         const int rmax = D - 1;                      // defensive: a rank can never leave the table
                         r00 = min(r00, rmax); r01 = min(r01, rmax); r10 = min(r10, rmax); r11 = min(r11, rmax);
-                        sim = w00 * table[r00 * TP + i];
-                        sim = fmaf(w01, table[r01 * TP + i], sim);
-                        sim = fmaf(w10, table[r10 * TP + i], sim);
-                        sim = fmaf(w11, table[r11 * TP + i], sim);
+                        sim = w00 * table[tix(r00, i)];
+                        sim = fmaf(w01, table[tix(r01, i)], sim);
+                        sim = fmaf(w10, table[tix(r10, i)], sim);
+                        sim = fmaf(w11, table[tix(r11, i)], sim);
                         tw[jj][0] = w00; tw[jj][1] = w01; tw[jj][2] = w10; tw[jj][3] = w11;
                         rk[jj][0] = (uint32_t)r00 | ((uint32_t)r01 << 16); rk[jj][1] = (uint32_t)r10 | ((uint32_t)r11 << 16);
                     }
@@ -353,7 +357,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
 #pragma unroll
             for (int jj = 0; jj < KW; jj++) { x[jj] = (act && warp + NWORK * jj < K) ? exp2f(x[jj] - M) : 0.f; sloc += x[jj]; }
             red_sum[warp * 32 + lane] = sloc;
-            for (int q = tid; q < D * TP; q += NT_WORK) Ti[q] = 0;
+            for (int q = tid; q < D * 8; q += NT_WORK) reinterpret_cast<int4 *>(Ti)[q] = make_int4(0, 0, 0, 0);
             named_bar(1, NT_WORK);
             float S = 0.f;
 #pragma unroll
@@ -374,7 +378,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     for (int tp = 0; tp < 4; tp++)
                         if (tw[jj][tp] != 0.f) {
                             const uint32_t r = (rk[jj][tp >> 1] >> ((tp & 1) * 16)) & 0xffffu;
-                            atomicAdd(&Ti[r * TP + i], __float2int_rn(av * tw[jj][tp] * FIX));
+                            atomicAdd(&Ti[tix((int)r, i)], __float2int_rn(av * tw[jj][tp] * FIX));
                         }
                 }
             }
@@ -407,7 +411,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 const int d0 = warp * 16 + hh * 8;
                 float f[8];
 #pragma unroll
-                for (int e = 0; e < 8; e++) f[e] = (act && d0 + e < D) ? (float)Ti[(d0 + e) * TP + i] * (1.0f / FIX) : 0.f;
+                for (int e = 0; e < 8; e++) f[e] = (act && d0 + e < D) ? (float)Ti[tix(d0 + e, i)] * (1.0f / FIX) : 0.f;
                 uint4 hi, lo;
                 split8(f, hi, lo);
                 const uint32_t off = (uint32_t)(d0 >> 6) * PANEL_B2 + (uint32_t)i * 128u + (uint32_t)((((d0 & 63) >> 3) ^ (i & 7)) << 4);

@@ -20,16 +20,20 @@ constexpr int NT = 256;
 constexpr int NBIN = 4096;
 constexpr int SMALL = 32;
 
-__device__ __forceinline__ float angle_key(int i, int W, const GeomCfg &gc, float ex, float ey, float a0, bool parallel, float span) {
-    const float px = pix2coord(i % W, gc.ds, gc.r), py = pix2coord(i / W, gc.ds, gc.r);
-    float u;                                   // in [0, 1)
-    if (parallel) {
-        u = 0.5f + 0.5f * ((px - 0.5f * (gc.xmin + gc.xmax)) * (-ey) + (py - 0.5f * (gc.ymin + gc.ymax)) * ex) / span;
-    } else {
-        float ang = atan2f(py - ey, px - ex) - a0;         // relative to the image centre: the cut is behind the epipole
-        if (ang < -3.14159265f) ang += 6.28318531f;
-        if (ang >= 3.14159265f) ang -= 6.28318531f;
-        u = (ang + 3.14159265f) * (1.f / 6.28318531f);
+// Monotone pseudo-angle of (u, v) in [-2, 2] (diamond angle): same ordering as atan2(v, u) at the price of one division.
+__device__ __forceinline__ float pseudo_angle(float u, float v) {
+    const float p = __fdividef(v, fabsf(u) + fabsf(v) + 1e-30f);
+    return u >= 0.f ? p : (v >= 0.f ? 2.f - p : -2.f - p);
+}
+// key in [0,1): position of the pixel centre (px, py) inside the image's span [lo, lo + 1/inv_span] of the pseudo-angle
+// around the epipole, measured from the direction (cdx, cdy) epipole -> image centre (so the cut lies behind the epipole);
+// for an epipole at infinity: the offset across the parallel epipolar lines of direction (cdx, cdy)
+__device__ __forceinline__ float angle_key(float px, float py, float ex, float ey, float cdx, float cdy, bool parallel, float lo, float inv_span) {
+    float u;
+    if (parallel) u = (px * (-cdy) + py * cdx - lo) * inv_span;
+    else {
+        const float dx = px - ex, dy = py - ey;
+        u = (pseudo_angle(dx * cdx + dy * cdy, dy * cdx - dx * cdy) - lo) * inv_span;
     }
     u = fminf(fmaxf(u, 0.f), 0.99999f);
     if (!(u == u)) u = 0.f;
@@ -51,8 +55,11 @@ struct StageArgs {
     __nv_bfloat16 *planes;            // [4][N*HW][C]: ref_hi, ref_lo, src_hi, src_lo
     const float *P_ref, *P_src;       // may be null (injected locations): no order, no pair constants
     PairGeom *pair_geom;              // [N]
-    uint16_t *order, *order_tmp;      // [N][HW]
+    uint16_t *order;                  // [N][HW]
     int *zero_words;                  // tile counter, error word
+    float *order_key;                 // optional [N][32]: key of the cached (order, pair constants); null = rebuild every call
+    const float *Wf;                  // optional [C][C] folded z weight -> bf16 (hi, lo) planes w_planes [2][C][C]
+    __nv_bfloat16 *w_planes;
     int N, C, H, W;
     int do_ref, do_src, do_order;
     GeomCfg gc;
@@ -60,7 +67,8 @@ struct StageArgs {
 
 __global__ void __launch_bounds__(stg::NT) epi_stage_kernel(const StageArgs s) {
     using namespace stg;
-    __shared__ __align__(16) float tile[64][65];          // transposition tile; the order blocks reuse it as histogram
+    extern __shared__ __align__(16) uint8_t dyn[];        // transposition tile [64][65] fp32 | order blocks: histogram + pixel list
+    float (*tile)[65] = reinterpret_cast<float (*)[65]>(dyn);
     const int t = threadIdx.x;
     const int H = s.H, W = s.W, HW = H * W, C = s.C;
     const int nord = s.do_order ? s.N : 0;
@@ -70,14 +78,32 @@ __global__ void __launch_bounds__(stg::NT) epi_stage_kernel(const StageArgs s) {
         // ------------------------------------------------------------------------------------------------
         // pair constants + epipolar-angle order of the pair's reference pixels
         // ------------------------------------------------------------------------------------------------
-        int *hist = reinterpret_cast<int *>(&tile[0][0]);              // NBIN counts -> offsets (16 KB of the 16.6 KB)
-        __shared__ float s_e[4];
+        int *hist = reinterpret_cast<int *>(dyn);                      // NBIN counts -> offsets
+        uint16_t *lst = reinterpret_cast<uint16_t *>(dyn + NBIN * 4);  // [HW] pixels grouped by bin (then sorted inside each bin)
+        __shared__ float s_e[8];                                  // [7]: cache hit
         __shared__ int s_warp[NT / 32];
         __shared__ int s_big[64], s_nbig;
 #ifdef EPI_PIPE_TIMERS
         long long st_prev = clock64();
 #endif
         const int n = blockIdx.x;
+        // cached order: the key is (P_ref, P_src, geometry configuration); an unchanged camera pair costs 32 compares
+        float my_key = 0.f;
+        if (t < 32) {
+            if (t < 12) my_key = s.P_ref[12 * n + t];
+            else if (t < 24) my_key = s.P_src[12 * n + t - 12];
+            else if (t == 24) my_key = (float)H;
+            else if (t == 25) my_key = (float)W;
+            else if (t == 26) my_key = s.gc.ds;
+            else if (t == 27) my_key = s.gc.r;
+            else if (t == 28) my_key = 1.f;                      // valid marker (a zero-initialised cache never matches)
+            if (s.order_key) {
+                const bool same = __float_as_uint(s.order_key[32 * n + t]) == __float_as_uint(my_key);
+                if (__all_sync(0xffffffffu, same)) s_e[7] = 1.f; else s_e[7] = 0.f;
+            } else s_e[7] = 0.f;
+        }
+        __syncthreads();
+        if (s_e[7] != 0.f) return;                               // hit: order and pair constants are already in place
         if (t == 0) {
             const float *P1 = s.P_ref + 12 * n, *P2 = s.P_src + 12 * n;
             PairGeom g;
@@ -97,21 +123,52 @@ __global__ void __launch_bounds__(stg::NT) epi_stage_kernel(const StageArgs s) {
             for (int r = 0; r < 3; r++) e[r] = (double)P1[r * 4] * cs[0] + (double)P1[r * 4 + 1] * cs[1] + (double)P1[r * 4 + 2] * cs[2] + (double)P1[r * 4 + 3];
             const double cx = 0.5 * ((double)s.gc.xmin + s.gc.xmax), cy = 0.5 * ((double)s.gc.ymin + s.gc.ymax);
             const double nrm = fabs(e[0]) + fabs(e[1]) + 1e-300;
+            // range of the key over the image: the four corners bound it unless the epipole lies inside the image
+            const float cxs[4] = {s.gc.xmin, s.gc.xmax, s.gc.xmin, s.gc.xmax}, cys[4] = {s.gc.ymin, s.gc.ymin, s.gc.ymax, s.gc.ymax};
+            float lo = 1e30f, hi = -1e30f, exf = 0.f, eyf = 0.f, cdx, cdy, par;
             if (!(fabs(e[2]) > 1e-9 * nrm)) {        // epipole at infinity (or NaN): parallel lines, sort by the offset across them
-                s_e[0] = (float)(e[0] / nrm); s_e[1] = (float)(e[1] / nrm); s_e[2] = 0.f; s_e[3] = 1.f;
+                cdx = (float)(e[0] / nrm); cdy = (float)(e[1] / nrm); par = 1.f;
+                for (int q = 0; q < 4; q++) { const float v = cxs[q] * (-cdy) + cys[q] * cdx; lo = fminf(lo, v); hi = fmaxf(hi, v); }
             } else {
                 const double ex = e[0] / e[2], ey = e[1] / e[2];
-                s_e[0] = (float)ex; s_e[1] = (float)ey; s_e[2] = (float)atan2(cy - ey, cx - ex); s_e[3] = 0.f;
+                const double dn = sqrt((cx - ex) * (cx - ex) + (cy - ey) * (cy - ey)) + 1e-300;
+                exf = (float)ex; eyf = (float)ey; cdx = (float)((cx - ex) / dn); cdy = (float)((cy - ey) / dn); par = 0.f;
+                const bool inside = ex >= s.gc.xmin && ex <= s.gc.xmax && ey >= s.gc.ymin && ey <= s.gc.ymax;
+                if (inside) { lo = -2.f; hi = 2.f; }
+                else
+                    for (int q = 0; q < 4; q++) {
+                        const float dx = cxs[q] - exf, dy = cys[q] - eyf;
+                        const float v = pseudo_angle(dx * cdx + dy * cdy, dy * cdx - dx * cdy);
+                        lo = fminf(lo, v); hi = fmaxf(hi, v);
+                    }
             }
+            if (!(hi > lo)) { lo = 0.f; hi = 1.f; }
+            s_e[0] = exf; s_e[1] = eyf; s_e[2] = cdx; s_e[3] = cdy; s_e[4] = par; s_e[5] = lo; s_e[6] = 1.f / ((hi - lo) * 1.0001f + 1e-20f);
             s_nbig = 0;
         }
         for (int b = t; b < NBIN; b += NT) hist[b] = 0;
         __syncthreads();
         ST(0);
-        const float ex = s_e[0], ey = s_e[1], a0 = s_e[2];
-        const bool parallel = s_e[3] != 0.f;
-        const float span = fabsf(s.gc.xmax - s.gc.xmin) + fabsf(s.gc.ymax - s.gc.ymin) + 1.f;
-        for (int i = t; i < HW; i += NT) atomicAdd(&hist[(int)(angle_key(i, W, s.gc, ex, ey, a0, parallel, span) * (float)NBIN)], 1);
+        const float ex = s_e[0], ey = s_e[1], cdx = s_e[2], cdy = s_e[3], klo = s_e[5], kinv = s_e[6];
+        const bool parallel = s_e[4] != 0.f;
+        // bins of this thread's pixels (i = t + 256 m), kept in registers between the two passes
+        constexpr int MAXPT = 64;                                        // H*W <= 16384
+        const int npt = (HW - t + NT - 1) / NT;
+        uint16_t bins[MAXPT];
+        {
+            int x = t % W, y = t / W;
+            const int sx = NT % W, sy = NT / W;
+#pragma unroll 4
+            for (int m = 0; m < MAXPT; m++) {
+                if (m < npt) {
+                    const int b = (int)(angle_key(pix2coord(x, s.gc.ds, s.gc.r), pix2coord(y, s.gc.ds, s.gc.r), ex, ey, cdx, cdy, parallel, klo, kinv) * (float)NBIN);
+                    bins[m] = (uint16_t)b;
+                    atomicAdd(&hist[b], 1);
+                    x += sx; y += sy;
+                    if (x >= W) { x -= W; y++; }
+                }
+            }
+        }
         __syncthreads();
         ST(1);
         // exclusive scan over the bins: 16 consecutive bins per thread, then a block scan of the partial sums
@@ -132,55 +189,52 @@ __global__ void __launch_bounds__(stg::NT) epi_stage_kernel(const StageArgs s) {
         for (int q = 0; q < PER; q++) { hist[t * PER + q] = base; base += loc[q]; }
         __syncthreads();
         ST(2);
-        // placement (arbitrary order inside a bin) into the scratch list
-        uint16_t *tmp = s.order_tmp + (size_t)n * HW, *ord = s.order + (size_t)n * HW;
-        for (int i = t; i < HW; i += NT) {
-            const int b = (int)(angle_key(i, W, s.gc, ex, ey, a0, parallel, span) * (float)NBIN);
-            tmp[atomicAdd(&hist[b], 1)] = (uint16_t)i;
-        }
+        // placement (arbitrary order inside a bin) into the shared list
+#pragma unroll 4
+        for (int m = 0; m < MAXPT; m++)
+            if (m < npt) lst[atomicAdd(&hist[bins[m]], 1)] = (uint16_t)(t + NT * m);
         __syncthreads();
         ST(3);
-        // inside every bin: ascending pixel index (insertion sort; bins hold ~HW/4096 entries)
+        // inside every bin: ascending pixel index (in-place insertion sort; bins hold ~HW/4096 entries)
+        uint16_t *ord = s.order + (size_t)n * HW;
         {
             int st0 = start0;
-#pragma unroll 1
+#pragma unroll
             for (int q = 0; q < PER; q++) {
                 const int len = loc[q];
                 if (len > SMALL) {
                     const int slot = atomicAdd(&s_nbig, 1);
                     if (slot < 64) s_big[slot] = t * PER + q;
-                } else if (len > 0) {
-                    uint16_t v[SMALL];
-                    for (int e = 0; e < len; e++) {
-                        const uint16_t x = tmp[st0 + e];
+                } else {
+                    for (int e = 1; e < len; e++) {
+                        const uint16_t xv = lst[st0 + e];
                         int p = e;
-                        while (p > 0 && v[p - 1] > x) { v[p] = v[p - 1]; p--; }
-                        v[p] = x;
+                        while (p > 0 && lst[st0 + p - 1] > xv) { lst[st0 + p] = lst[st0 + p - 1]; p--; }
+                        lst[st0 + p] = xv;
                     }
-                    for (int e = 0; e < len; e++) ord[st0 + e] = v[e];
                 }
                 st0 += len;
             }
         }
         __syncthreads();
         ST(4);
-        // degenerate cameras only: big bins are ranked by counting, the whole block per bin
         const int nbig = s_nbig < 64 ? s_nbig : 64;
+        for (int i = t; i < HW; i += NT) ord[i] = lst[i];
+        // degenerate cameras only: big bins are ranked by counting (unique values), the whole block per bin, straight to global
         for (int bb = 0; bb < nbig; bb++) {
             const int b = s_big[bb];
-            const int end = hist[b];                     // after placement: offset = end of the bin
-            // start = end of the previous non-empty prefix: recompute from the neighbour (bin b-1's end), or 0
-            const int beg = b == 0 ? 0 : hist[b - 1];
+            const int end = hist[b], beg = b == 0 ? 0 : hist[b - 1];     // after placement hist[b] = end of bin b
+            __syncthreads();
             for (int e = beg + t; e < end; e += NT) {
-                const uint16_t x = tmp[e];
+                const uint16_t xv = lst[e];
                 int r = 0;
-                for (int f = beg; f < end; f++) r += tmp[f] < x;
-                ord[beg + r] = x;
+                for (int f = beg; f < end; f++) r += lst[f] < xv;
+                ord[beg + r] = xv;
             }
         }
-        if (s_nbig > 64) {                               // pathological: more than 64 big bins — keep the scratch order
+        if (s.order_key) {                                       // publish the key last (same stream => ordered for the next call)
             __syncthreads();
-            for (int i = t; i < HW; i += NT) ord[i] = tmp[i];
+            if (t < 32) s.order_key[32 * n + t] = my_key;
         }
         return;
     }
@@ -191,6 +245,26 @@ __global__ void __launch_bounds__(stg::NT) epi_stage_kernel(const StageArgs s) {
     const int tiles_p = (HW + 63) / 64, tiles_c = (C + 63) / 64;
     const int per_map = tiles_p * tiles_c * s.N;
     int lin = (int)blockIdx.x - nord;
+    if (lin >= 2 * per_map) {
+        // folded z weight [C out][C in] fp32 -> bf16 (hi, lo) planes (B operand of the z GEMM), 8 elements per thread
+        const size_t e0 = ((size_t)(lin - 2 * per_map) * NT + t) * 8, tot = (size_t)C * C;
+        if (e0 < tot) {
+            const float4 a4 = __ldg(reinterpret_cast<const float4 *>(s.Wf + e0)), b4 = __ldg(reinterpret_cast<const float4 *>(s.Wf + e0 + 4));
+            const float f[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const __nv_bfloat162 hv = __floats2bfloat162_rn(f[2 * u], f[2 * u + 1]);
+                const float2 hf = __bfloat1622float2(hv);
+                const __nv_bfloat162 lv = __floats2bfloat162_rn(f[2 * u] - hf.x, f[2 * u + 1] - hf.y);
+                h[u] = *reinterpret_cast<const uint32_t *>(&hv);
+                l[u] = *reinterpret_cast<const uint32_t *>(&lv);
+            }
+            *reinterpret_cast<uint4 *>(s.w_planes + e0) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4 *>(s.w_planes + tot + e0) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        return;
+    }
     int map = 0;
     if (s.do_ref && s.do_src) { map = lin >= per_map; lin -= map * per_map; }
     else map = s.do_src ? 1 : 0;
@@ -257,16 +331,27 @@ __global__ void __launch_bounds__(stg::NT) epi_stage_kernel(const StageArgs s) {
 
 cudaError_t launch_stage(const float *ref, const int64_t ref_stride[4], const float *src, const int64_t src_stride[4],
                          __nv_bfloat16 *planes, const float *P_ref, const float *P_src, PairGeom *pair_geom, uint16_t *order,
-                         uint16_t *order_tmp, int *zero_words, int N, int C, int H, int W, const GeomCfg &gc, cudaStream_t st) {
+                         float *order_key, const float *Wf, __nv_bfloat16 *w_planes, int *zero_words, int N, int C, int H, int W,
+                         const GeomCfg &gc, cudaStream_t st) {
     StageArgs s;
     s.ref = ref; s.src = src;
     for (int i = 0; i < 4; i++) { s.ref_stride[i] = ref_stride[i]; s.src_stride[i] = src_stride[i]; }
-    s.planes = planes; s.P_ref = P_ref; s.P_src = P_src; s.pair_geom = pair_geom; s.order = order; s.order_tmp = order_tmp;
+    s.planes = planes; s.P_ref = P_ref; s.P_src = P_src; s.pair_geom = pair_geom; s.order = order; s.order_key = order_key; s.Wf = Wf; s.w_planes = w_planes;
     s.zero_words = zero_words; s.N = N; s.C = C; s.H = H; s.W = W; s.gc = gc;
     s.do_ref = 1; s.do_src = 1; s.do_order = (P_ref && P_src && order) ? 1 : 0;
     const int tiles = ((H * W + 63) / 64) * ((C + 63) / 64) * N;
-    const int grid = (s.do_order ? N : 0) + 2 * tiles;
-    epi_stage_kernel<<<grid, stg::NT, 0, st>>>(s);
+    const int wblocks = (Wf && w_planes) ? (C * C / 8 + stg::NT - 1) / stg::NT : 0;        // C % 8 == 0
+    const int grid = (s.do_order ? N : 0) + 2 * tiles + wblocks;
+    // dynamic shared memory: the transposition tile, or (order blocks) 16 KB histogram + 2 B per pixel
+    size_t smem = 64 * 65 * sizeof(float);
+    if (s.do_order && (size_t)stg::NBIN * 4 + (size_t)H * W * 2 > smem) smem = (size_t)stg::NBIN * 4 + (size_t)H * W * 2;
+    static thread_local size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(epi_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set = smem;
+    }
+    epi_stage_kernel<<<grid, stg::NT, smem, st>>>(s);
     return cudaGetLastError();
 }
 

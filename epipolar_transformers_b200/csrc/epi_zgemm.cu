@@ -26,7 +26,7 @@ constexpr int NT = 256;
 constexpr uint32_t A_PLANE = 16384;                 // 128 rows x 128 B
 constexpr uint32_t B_PLANE = 32768;                 // 256 rows x 128 B
 constexpr uint32_t STAGE = 2 * A_PLANE + 2 * B_PLANE;   // 96 KB
-constexpr uint32_t SMEM_ALLOC = 2 * STAGE + 1024 + 64;
+constexpr uint32_t SMEM_ALLOC = 2 * STAGE + 1024 + 128;
 
 // 2-D tiled TMA load of a [128 rows x 64 bf16] box into a swizzled panel, completion counted on `bar`
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
@@ -38,12 +38,14 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
 }  // namespace zg
 
 __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z, const __grid_constant__ CUtensorMap tm_hi,
-                                                              const __grid_constant__ CUtensorMap tm_lo, const int use_tma) {
+                                                              const __grid_constant__ CUtensorMap tm_lo,
+                                                              const __grid_constant__ CUtensorMap tw_hi,
+                                                              const __grid_constant__ CUtensorMap tw_lo) {
     using namespace zg;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * STAGE);       // [0,1] MMAs done with stage, [2] all, [3] TMA landed
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * STAGE + 32);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * STAGE);       // [0,1] stage landed (TMA), [2,3] MMAs done with stage, [4] all MMAs done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * STAGE + 64);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = z.C, HW = z.HW, W = z.W;
     const int tiles = (HW + 127) / 128;
@@ -52,73 +54,37 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
     const __nv_bfloat16 *xh = z.x_hi + (size_t)n * HW * C, *xl = z.x_lo + (size_t)n * HW * C;
 
     if (warp == 0) tmem_alloc(tmem_slot, 256);
-    if (tid == 32) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1); mbar_fence_init(); }
-    if (tid == 0 && use_tma) {
+    if (tid == 32) { for (int i = 0; i < 5; i++) mbar_init(&bars[i], 1); mbar_fence_init(); }
+    if (tid == 64) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tw_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tw_lo) : "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    for (int q = 0; q < nq; q++) {
-        const uint32_t buf = q & 1;
-        uint8_t *st = smem + buf * STAGE;
-        if (q >= 2) { for (uint32_t it = 0; !mbar_try_wait(&bars[buf], ((q >> 1) + 1) & 1); ++it) if (it > (1u << 26)) __trap(); }
-        // A: 128 pixel rows x 64 channels of both planes
-        if (use_tma) {
-            if (tid == 0) {                                     // one thread arms the barrier and issues both boxes
-                mbar_arrive_expect_tx(&bars[3], 2 * A_PLANE);
-                tma_load_2d(st, &tm_hi, q * 64, n * HW + p0, &bars[3]);
-                tma_load_2d(st + A_PLANE, &tm_lo, q * 64, n * HW + p0, &bars[3]);
-            }
-        } else {                                                // 16-byte chunks, 8 lanes per row
-            const int j = tid & 7;
-#pragma unroll
-            for (int it = 0; it < 8; it++) {
-                const int plane = it >> 2, r = (it & 3) * 32 + (tid >> 3), p = p0 + r, c0 = q * 64 + j * 8;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (p < HW && c0 < C) v = __ldg(reinterpret_cast<const uint4 *>((plane ? xl : xh) + (size_t)p * C + c0));
-                *reinterpret_cast<uint4 *>(st + plane * A_PLANE + r * 128u + ((j ^ (r & 7)) << 4)) = v;
-            }
-        }
-        // B: Wf rows o (out channels) x 64 input channels, split to (hi, lo) on the fly
-        {
-            const int j = tid & 7;
-#pragma unroll
-            for (int it = 0; it < 8; it++) {
-                const int o = it * 32 + (tid >> 3), c0 = q * 64 + j * 8;
-                float f[8];
-#pragma unroll
-                for (int u = 0; u < 8; u++) f[u] = 0.f;
-                if (o < C && c0 < C) {
-                    const float4 a = __ldg(reinterpret_cast<const float4 *>(z.Wf + (size_t)o * C + c0));
-                    const float4 b = __ldg(reinterpret_cast<const float4 *>(z.Wf + (size_t)o * C + c0 + 4));
-                    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-                }
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const __nv_bfloat162 hv = __floats2bfloat162_rn(f[2 * u], f[2 * u + 1]);
-                    const float2 hf = __bfloat1622float2(hv);
-                    const __nv_bfloat162 lv = __floats2bfloat162_rn(f[2 * u] - hf.x, f[2 * u + 1] - hf.y);
-                    h[u] = *reinterpret_cast<const uint32_t *>(&hv);
-                    l[u] = *reinterpret_cast<const uint32_t *>(&lv);
-                }
-                const uint32_t off = 2 * A_PLANE + o * 128u + ((j ^ (o & 7)) << 4);
-                *reinterpret_cast<uint4 *>(st + off) = make_uint4(h[0], h[1], h[2], h[3]);
-                *reinterpret_cast<uint4 *>(st + B_PLANE + off) = make_uint4(l[0], l[1], l[2], l[3]);
-            }
-        }
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncthreads();
-        tc_fence_after();
-        if (tid == 0) {
-            if (use_tma) { for (uint32_t it = 0; !mbar_try_wait(&bars[3], q & 1); ++it) if (it > (1u << 26)) __trap(); }
-            const uint32_t idesc = make_idesc_bf16(128, z.Npad, 0, 0);
-            const uint32_t sa = smem_u32(st), sb = sa + 2 * A_PLANE;
+    // One thread drives the whole main loop: TMA loads of the (A, W) panels into a 2-stage ring, tcgen05.mma issue, commits.
+    // A: 128 pixel rows x 64 channels of the (hi, lo) planes of x;  B: C output rows x 64 input channels of the (hi, lo) planes of Wf.
+    if (tid == 0) {
+        auto load = [&](int q) {
+            uint8_t *st = smem + (q & 1) * STAGE;
+            mbar_arrive_expect_tx(&bars[q & 1], 2 * A_PLANE + 2 * B_PLANE);
+            tma_load_2d(st, &tm_hi, q * 64, n * HW + p0, &bars[q & 1]);
+            tma_load_2d(st + A_PLANE, &tm_lo, q * 64, n * HW + p0, &bars[q & 1]);
+            tma_load_2d(st + 2 * A_PLANE, &tw_hi, q * 64, 0, &bars[q & 1]);
+            tma_load_2d(st + 2 * A_PLANE + B_PLANE, &tw_lo, q * 64, 0, &bars[q & 1]);
+        };
+        load(0);
+        if (nq > 1) load(1);
+        const uint32_t idesc = make_idesc_bf16(128, z.Npad, 0, 0);
+        for (int q = 0; q < nq; q++) {
+            const uint32_t buf = q & 1;
+            for (uint32_t it = 0; !mbar_try_wait(&bars[buf], (q >> 1) & 1); ++it) if (it > (1u << 24)) __trap();
+            tc_fence_after();
+            const uint32_t sa = smem_u32(smem + buf * STAGE), sb = sa + 2 * A_PLANE;
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
                 const uint64_t a_hi = make_smem_desc(sa + ks * 32, 16, 1024), a_lo = make_smem_desc(sa + A_PLANE + ks * 32, 16, 1024);
@@ -127,11 +93,15 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
                 mma_bf16(tmem, a_hi, b_lo, idesc, 1u);
                 mma_bf16(tmem, a_lo, b_hi, idesc, 1u);
             }
-            mma_commit(&bars[buf]);
+            mma_commit(&bars[2 + buf]);
+            if (q + 2 < nq) {
+                for (uint32_t it = 0; !mbar_try_wait(&bars[2 + buf], (q >> 1) & 1); ++it) if (it > (1u << 24)) __trap();
+                load(q + 2);
+            }
         }
+        mma_commit(&bars[4]);
     }
-    if (tid == 0) mma_commit(&bars[2]);
-    for (uint32_t it = 0; !mbar_try_wait(&bars[2], 0); ++it) if (it > (1u << 26)) __trap();
+    for (uint32_t it = 0; !mbar_try_wait(&bars[4], 0); ++it) if (it > (1u << 24)) __trap();
     tc_fence_after();
 
     // epilogue: thread <-> pixel (TMEM lane), 32 output channels at a time
@@ -176,7 +146,7 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-bool zgemm_supported(int C) { return C % 16 == 0 && C >= 16 && C <= 256; }
+bool zgemm_supported(int C) { return C % 64 == 0 && C >= 64 && C <= 256; }   // whole 64-channel TMA panels
 
 namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -191,13 +161,13 @@ EncodeTiledFn encode_fn() {
     }();
     return fn;
 }
-// [rows = N*HW, cols = C] bf16 plane, box = 64 columns x 128 rows, 128-byte swizzle (what the UMMA K-major descriptor reads)
-bool make_plane_map(CUtensorMap *m, const __nv_bfloat16 *base, int rows, int C) {
+// [rows, cols = C] bf16 plane, box = 64 columns x box_rows rows, 128-byte swizzle (what the UMMA K-major descriptor reads)
+bool make_plane_map(CUtensorMap *m, const __nv_bfloat16 *base, int rows, int C, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn || C % 8 != 0) return false;
     const cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
     const cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-    const cuuint32_t box[2] = {64u, 128u};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1u, 1u};
     return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16 *>(base), dims, strides, box, estr,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -207,13 +177,23 @@ bool make_plane_map(CUtensorMap *m, const __nv_bfloat16 *base, int rows, int C) 
 
 cudaError_t launch_zgemm(const ZGemmArgs &z, cudaStream_t st) {
     const int tiles = (z.HW + 127) / 128;
-    cudaError_t e = cudaFuncSetAttribute(epi_zgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zg::SMEM_ALLOC);
-    if (e != cudaSuccess) return e;
-    CUtensorMap tm_hi, tm_lo;
-    memset(&tm_hi, 0, sizeof(tm_hi)); memset(&tm_lo, 0, sizeof(tm_lo));
-    // TMA needs whole 64-column boxes inside the row pitch; otherwise the LDG path stages A
-    const int use_tma = (z.C % 64 == 0) && make_plane_map(&tm_hi, z.x_hi, z.N * z.HW, z.C) && make_plane_map(&tm_lo, z.x_lo, z.N * z.HW, z.C);
-    epi_zgemm_kernel<<<z.N * tiles, zg::NT, zg::SMEM_ALLOC, st>>>(z, tm_hi, tm_lo, use_tma);
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(epi_zgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zg::SMEM_ALLOC);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    // tensor maps are a pure function of (pointers, shape): keep the last set per host thread
+    struct MapCache { const void *xh, *wh; int rows, C; CUtensorMap m[4]; };
+    static thread_local MapCache mc = {nullptr, nullptr, 0, 0, {}};
+    if (mc.xh != z.x_hi || mc.wh != z.w_hi || mc.rows != z.N * z.HW || mc.C != z.C) {
+        const int wrows = z.C < 256 ? z.C : 256;
+        if (!make_plane_map(&mc.m[0], z.x_hi, z.N * z.HW, z.C, 128) || !make_plane_map(&mc.m[1], z.x_lo, z.N * z.HW, z.C, 128) ||
+            !make_plane_map(&mc.m[2], z.w_hi, z.C, z.C, wrows) || !make_plane_map(&mc.m[3], z.w_lo, z.C, z.C, wrows))
+            return cudaErrorInvalidValue;
+        mc.xh = z.x_hi; mc.wh = z.w_hi; mc.rows = z.N * z.HW; mc.C = z.C;
+    }
+    epi_zgemm_kernel<<<z.N * tiles, zg::NT, zg::SMEM_ALLOC, st>>>(z, mc.m[0], mc.m[1], mc.m[2], mc.m[3]);
     return cudaGetLastError();
 }
 

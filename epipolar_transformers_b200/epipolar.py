@@ -46,17 +46,33 @@ def _check_feat(name, t):
         raise TypeError("%s must be float32 (got %s)" % (name, t.dtype))
 
 
+class FusionState:
+    """Persistent scratch of one caller (module) on one device: the workspace, the cross-call cache of the C ABI
+    (pixel order + pair constants keyed by the camera matrices) and the prepared parameter block.  Re-using it removes
+    the per-call allocations and lets an unchanged camera pair skip its setup work.  A state must not be shared by
+    calls that can run concurrently (different streams / threads): give each its own."""
+
+    __slots__ = ("key", "ws", "cache", "params")
+
+    def __init__(self):
+        self.key = None
+        self.ws = None
+        self.cache = None
+        self.params = None
+
+
 def epipolar_fusion(feat_ref, feat_src, P_ref, P_src, *, K, downsample=4.0, img_scale=1.0,
                     softmax_scale=0.125, correct_normalize=False, align_corners=False,
                     z_folded=None, z_residual=False, add_ref_residual=False,
                     sample_locs_in=None, want_attn=True, want_corr=True, want_locs=False,
-                    variant="auto", out=None):
+                    variant="auto", out=None, state: Optional[FusionState] = None):
     """Functional form of the fused forward.  Returns (out, corr_pos|None, attn|None, sample_locs|None).
 
     feat_ref/feat_src: CUDA float32 [N,C,H,W] (NCHW or channels_last strides).
     P_ref/P_src: [N,3,4] (cast to float32 like modeling/model.py:183-195).
     z_folded: optional (Wf [C,C], bf [C]) from `fold_z_bn` (eval-mode epilogue, epipolar.py:249-253).
     sample_locs_in: optional [K,N,H,W,2] normalised locations replacing the fused geometry.
+    state: optional FusionState (persistent workspace + camera-keyed cache); without it scratch is allocated per call.
     """
     lib = _lib.load()
     _check_feat("feat_ref", feat_ref)
@@ -66,8 +82,10 @@ def epipolar_fusion(feat_ref, feat_src, P_ref, P_src, *, K, downsample=4.0, img_
     N, C, H, W = feat_ref.shape
     dev = feat_ref.device
     if sample_locs_in is None:
-        P_ref = P_ref.to(device=dev, dtype=torch.float32).contiguous()
-        P_src = P_src.to(device=dev, dtype=torch.float32).contiguous()
+        if P_ref.device != dev or P_ref.dtype != torch.float32 or not P_ref.is_contiguous():
+            P_ref = P_ref.to(device=dev, dtype=torch.float32).contiguous()
+        if P_src.device != dev or P_src.dtype != torch.float32 or not P_src.is_contiguous():
+            P_src = P_src.to(device=dev, dtype=torch.float32).contiguous()
         if tuple(P_ref.shape) != (N, 3, 4) or tuple(P_src.shape) != (N, 3, 4):
             raise ValueError("P_ref/P_src must be [N,3,4]")
     else:
@@ -80,30 +98,47 @@ def epipolar_fusion(feat_ref, feat_src, P_ref, P_src, *, K, downsample=4.0, img_
     corr = torch.empty((N, H, W, 2), device=dev, dtype=torch.float32) if want_corr else None
     locs = torch.empty((K, N, H, W, 2), device=dev, dtype=torch.float32) if want_locs else None
 
-    p = _lib.EpiFusionParams()
-    p.feat_ref = feat_ref.data_ptr(); p.ref_stride = _strides4(feat_ref)
-    p.feat_src = feat_src.data_ptr(); p.src_stride = _strides4(feat_src)
+    vcode = _lib.VARIANTS[variant] if isinstance(variant, str) else int(variant)
+    key = (dev, N, C, H, W, int(K), feat_ref.stride(), feat_src.stride(), out.stride(), z_folded is not None, vcode,
+           sample_locs_in is not None, float(downsample), float(img_scale), float(softmax_scale), bool(correct_normalize),
+           bool(align_corners), bool(z_residual), bool(add_ref_residual))
+    if state is not None and state.key == key:
+        p = state.params
+    else:
+        p = _lib.EpiFusionParams()
+        p.ref_stride = _strides4(feat_ref); p.src_stride = _strides4(feat_src); p.out_stride = _strides4(out)
+        p.N, p.C, p.H, p.W, p.K = N, C, H, W, int(K)
+        p.downsample = float(downsample); p.img_scale = float(img_scale)
+        p.eps = _EPSILON; p.softmax_scale = float(softmax_scale)
+        p.align_corners = int(bool(align_corners)); p.correct_normalize = int(bool(correct_normalize))
+        p.z_residual = int(bool(z_residual)); p.add_ref_residual = int(bool(add_ref_residual))
+        p.variant = vcode
+    p.feat_ref = feat_ref.data_ptr(); p.feat_src = feat_src.data_ptr()
     p.P_ref = P_ref.data_ptr() if sample_locs_in is None else None
     p.P_src = P_src.data_ptr() if sample_locs_in is None else None
     p.sample_locs_in = sample_locs_in.data_ptr() if sample_locs_in is not None else None
-    p.out = out.data_ptr(); p.out_stride = _strides4(out)
+    p.out = out.data_ptr()
     p.attn = attn.data_ptr() if attn is not None else None
     p.corr_pos = corr.data_ptr() if corr is not None else None
     p.sample_locs_out = locs.data_ptr() if locs is not None else None
     if z_folded is not None:
         wf, bf = z_folded
         p.z_weight_folded = wf.data_ptr(); p.z_bias_folded = bf.data_ptr()
-    p.N, p.C, p.H, p.W, p.K = N, C, H, W, int(K)
-    p.downsample = float(downsample); p.img_scale = float(img_scale)
-    p.eps = _EPSILON; p.softmax_scale = float(softmax_scale)
-    p.align_corners = int(bool(align_corners)); p.correct_normalize = int(bool(correct_normalize))
-    p.z_residual = int(bool(z_residual)); p.add_ref_residual = int(bool(add_ref_residual))
-    p.variant = _lib.VARIANTS[variant] if isinstance(variant, str) else int(variant)
-    nbytes = lib.epi_fusion_workspace_bytes(ctypes.byref(p))
     ws = None
-    if nbytes:
-        ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)      # caching allocator: stream-ordered, 512-B aligned
-        p.workspace = ws.data_ptr(); p.workspace_bytes = nbytes
+    if state is not None and state.key == key:
+        pass                                                       # workspace / cache pointers already in the block
+    else:
+        if state is not None:
+            cbytes = lib.epi_fusion_cache_bytes(ctypes.byref(p))
+            state.cache = torch.zeros(cbytes, device=dev, dtype=torch.uint8) if cbytes else None
+            p.cache = state.cache.data_ptr() if cbytes else None
+            p.cache_bytes = cbytes
+        nbytes = lib.epi_fusion_workspace_bytes(ctypes.byref(p))
+        if nbytes:
+            ws = torch.empty(nbytes, device=dev, dtype=torch.uint8)      # caching allocator: stream-ordered, 512-B aligned
+            p.workspace = ws.data_ptr(); p.workspace_bytes = nbytes
+        if state is not None:
+            state.ws = ws; state.params = p; state.key = key
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
         _lib.check(lib.epi_fusion_forward_f32(ctypes.byref(p), ctypes.c_void_p(stream)), "epi_fusion_forward_f32")
@@ -190,14 +225,29 @@ class Epipolar(nn.Module):
             self.z = nn.Conv2d(nf // ep.BOTTLENECK, nf, kernel_size=1, stride=1, padding=0, bias=True)
             self.bn = ZeroInitBN(nf)
         self._fold_cache = None
+        self._states = {}            # device -> FusionState (persistent workspace + camera-keyed cache)
 
     # -- eval-mode folding of z + BN, cached on parameter versions -------------------------------
     def _folded(self):
         ts = (self.z.weight, self.z.bias, self.bn.weight, self.bn.bias, self.bn.running_mean, self.bn.running_var)
         key = tuple((t.data_ptr(), t._version) for t in ts if t is not None)
+        dev = self.z.weight.device
+        cur = torch.cuda.current_stream(dev)
         if self._fold_cache is None or self._fold_cache[0] != key:
-            self._fold_cache = (key, fold_z_bn(self.z, self.bn))
-        return self._fold_cache[1]
+            folded = fold_z_bn(self.z, self.bn)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._fold_cache = (key, folded, ev, {cur.cuda_stream})
+        _, folded, ev, seen = self._fold_cache
+        if cur.cuda_stream not in seen:          # a consumer on another stream must not read the fold before it is written
+            cur.wait_event(ev)
+            seen.add(cur.cuda_stream)
+        return folded
+
+    def _state_for(self, t):
+        if not (isinstance(t, torch.Tensor) and t.is_cuda):
+            return None                                  # epipolar_fusion raises the proper error for CPU tensors
+        return self._states.setdefault((t.device, torch.cuda.current_stream(t.device).cuda_stream), FusionState())
 
     def forward(self, feat1, feat2, P1, P2, depth=None, camera=None, other_camera=None, ref1=None, ref2=None):
         """feat1/feat2: N x C x H x W; P1/P2: N x 3 x 4 (epipolar.py:82-89).
@@ -219,7 +269,8 @@ class Epipolar(nn.Module):
             align_corners=self.align_corners, z_folded=self._folded() if fold else None,
             z_residual=bool(ep.ZRESIDUAL) if fold else False,
             add_ref_residual=self.fuse_ref_residual and (fold or not has_z),
-            want_attn=self.emit_attn, want_corr=self.emit_corr, want_locs=want_locs, variant=self.variant)
+            want_attn=self.emit_attn, want_corr=self.emit_corr, want_locs=want_locs, variant=self.variant,
+            state=self._state_for(feat1))
         if has_z and not fold:
             # training-mode BN needs batch statistics (+ autograd to z/bn): keep conv/BN in PyTorch
             finalout = self.bn(self.z(out))

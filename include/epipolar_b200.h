@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define EPI_ABI_VERSION 1
+#define EPI_ABI_VERSION 2
 
 #define EPI_OK 0
 #define EPI_EINVAL (-1)       /* bad argument / unsupported shape */
@@ -76,6 +76,12 @@ typedef struct EpiFusionParams {
     int32_t add_ref_residual;     /* 1: also add feat_ref (the caller's `ret + feat`, resnet.py:388) */
     int32_t variant;              /* EPI_VARIANT_* */
     int32_t reserved[3];
+    /* ---- optional persistent state (ABI v2) -------------------------------------------- */
+    void *cache;                  /* device memory the caller keeps alive ACROSS calls and zero-fills once, or NULL.  Holds the
+                                     per-pair constants and the epipolar pixel order keyed by (P_ref, P_src, H, W, downsample,
+                                     img_scale): an unchanged camera pair skips their recomputation.  One cache per
+                                     (module, device, stream); never share it between concurrently running calls. */
+    size_t cache_bytes;           /* >= epi_fusion_cache_bytes(p) when cache != NULL */
 } EpiFusionParams;
 
 /* ABI version of the loaded library (== EPI_ABI_VERSION it was built with). */
@@ -86,6 +92,9 @@ const char *epi_last_error(void);
 
 /* Bytes of scratch the forward needs for these shapes/strides/flags (0 is possible). */
 size_t epi_fusion_workspace_bytes(const EpiFusionParams *p);
+
+/* Bytes of the optional persistent cache for these shapes (0 when the selected kernel keeps no cross-call state). */
+size_t epi_fusion_cache_bytes(const EpiFusionParams *p);
 
 /* The fused forward: geometry + K bilinear taps + softmax(QK)·V (+ z/BN epilogue, + residuals).
  * Replaces Epipolar.forward for ATTENTION='avg', SIMILARITY='dot', SOFTMAX_ENABLED.

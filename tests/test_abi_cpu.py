@@ -73,17 +73,23 @@ def test_workspace_plan(lib):
     m = 4 * 256 * 64 * 64 * 4
     order = 4 * 4096 * 2                                                     # pixel order list (u16)
     geom = 256                                                               # 4 pairs x 44 B of pair constants, 256-B granules
-    pipe = 2 * m + 256 + 2 * order + geom       # ref + src bf16 (hi, lo) planes, counter/error words, order + sort scratch
+    pipe = 2 * m + 256 + order + geom           # ref + src bf16 (hi, lo) planes, counter/error words, pixel order, pair constants
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == pipe
+    assert lib.epi_fusion_cache_bytes(ctypes.byref(p)) == 4 * 32 * 4 + geom + order      # keys + pair constants + order
+    p.cache = ctypes.addressof(buf)                                          # with a persistent cache they leave the workspace
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 2 * m + 256
+    p.cache = None
     p.z_weight_folded = ctypes.addressof(buf)
-    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == pipe + m      # + pre-z bf16 planes
+    wpl = 256 * 256 * 4                                                      # folded z weight as bf16 (hi, lo) planes
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == pipe + m + wpl    # + pre-z bf16 planes + weight planes
     p.variant = _lib.EPI_VARIANT_SECTOR
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 3 * m + 256 + order
+    assert lib.epi_fusion_cache_bytes(ctypes.byref(p)) == 0
     p.variant = _lib.EPI_VARIANT_TILE
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 2 * m + 256   # 4x8 block tiles: no ref planes / order list
     p.variant = _lib.EPI_VARIANT_AUTO
     p.src_stride = (ctypes.c_int64 * 4)(256 * 4096, 1, 64 * 256, 256)      # channels_last
-    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == pipe + m      # tensor-core kernels stage bf16 (hi, lo) planes
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == pipe + m + wpl    # tensor-core kernels stage bf16 (hi, lo) planes
     p.variant = _lib.EPI_VARIANT_WARP
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == m             # warp kernel reads channels_last in place
 

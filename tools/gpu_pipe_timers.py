@@ -14,9 +14,10 @@ W = H
 P1, P2 = syn.pairs_from_ring(N, 4 * H)
 f1 = torch.relu(torch.randn(N, C, H, W, device="cuda")); f2 = torch.relu(torch.randn(N, C, H, W, device="cuda"))
 P1 = torch.from_numpy(P1.astype(np.float32)).cuda(); P2 = torch.from_numpy(P2.astype(np.float32)).cuda()
+wf = torch.randn(C, C, device="cuda") * 0.05; bf = torch.randn(C, device="cuda")
 buf = (ctypes.c_ulonglong * 32)()
 for it in range(3):
-    epi.epipolar_fusion(f1, f2, P1, P2, K=K, correct_normalize=True, variant="pipe")
+    epi.epipolar_fusion(f1, f2, P1, P2, K=K, correct_normalize=True, variant="pipe", z_folded=(wf, bf), z_residual=True)
     torch.cuda.synchronize()
     lib.epi_pipe_timers_read(buf, 1)
 v = np.array(list(buf), dtype=np.float64)
