@@ -17,6 +17,7 @@ VARIANTS = {"auto": EPI_VARIANT_AUTO, "warp": EPI_VARIANT_WARP, "tile": EPI_VARI
             "pipe": EPI_VARIANT_PIPE}
 
 EXPORTS = ("epi_version", "epi_last_error", "epi_fusion_workspace_bytes", "epi_fusion_cache_bytes", "epi_fusion_forward_f32",
+           "epi_fusion_backward_workspace_bytes", "epi_fusion_backward_f32",
            "epi_sample_locs_f32", "epi_fold_z_bn_f32", "epi_last_launch_count", "epi_umma_selftest",
            "epi_kernel_timing_enable", "epi_kernel_timing_last_ms")
 
@@ -38,6 +39,25 @@ class EpiFusionParams(ctypes.Structure):
         ("align_corners", ctypes.c_int32), ("correct_normalize", ctypes.c_int32), ("z_residual", ctypes.c_int32),
         ("add_ref_residual", ctypes.c_int32), ("variant", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3),
         ("cache", ctypes.c_void_p), ("cache_bytes", ctypes.c_size_t),
+    ]
+
+
+class EpiFusionBwdParams(ctypes.Structure):
+    """Field-for-field mirror of `struct EpiFusionBwdParams` (include/epipolar_b200.h)."""
+    _fields_ = [
+        ("feat_ref", ctypes.c_void_p), ("ref_stride", ctypes.c_int64 * 4),
+        ("feat_src", ctypes.c_void_p), ("src_stride", ctypes.c_int64 * 4),
+        ("P_ref", ctypes.c_void_p), ("P_src", ctypes.c_void_p), ("sample_locs_in", ctypes.c_void_p),
+        ("attn", ctypes.c_void_p),
+        ("grad_out", ctypes.c_void_p), ("gout_stride", ctypes.c_int64 * 4),
+        ("grad_attn", ctypes.c_void_p),
+        ("grad_ref", ctypes.c_void_p), ("gref_stride", ctypes.c_int64 * 4),
+        ("grad_src", ctypes.c_void_p), ("gsrc_stride", ctypes.c_int64 * 4),
+        ("workspace", ctypes.c_void_p), ("workspace_bytes", ctypes.c_size_t),
+        ("N", ctypes.c_int32), ("C", ctypes.c_int32), ("H", ctypes.c_int32), ("W", ctypes.c_int32), ("K", ctypes.c_int32),
+        ("downsample", ctypes.c_float), ("img_scale", ctypes.c_float), ("eps", ctypes.c_float), ("softmax_scale", ctypes.c_float),
+        ("align_corners", ctypes.c_int32), ("correct_normalize", ctypes.c_int32),
+        ("grad_keys", ctypes.c_int32), ("grad_vals", ctypes.c_int32), ("reserved", ctypes.c_int32 * 4),
     ]
 
 
@@ -66,6 +86,10 @@ def load():
     lib.epi_fusion_cache_bytes.argtypes = [ctypes.POINTER(EpiFusionParams)]
     lib.epi_fusion_forward_f32.restype = ctypes.c_int
     lib.epi_fusion_forward_f32.argtypes = [ctypes.POINTER(EpiFusionParams), ctypes.c_void_p]
+    lib.epi_fusion_backward_workspace_bytes.restype = ctypes.c_size_t
+    lib.epi_fusion_backward_workspace_bytes.argtypes = [ctypes.POINTER(EpiFusionBwdParams)]
+    lib.epi_fusion_backward_f32.restype = ctypes.c_int
+    lib.epi_fusion_backward_f32.argtypes = [ctypes.POINTER(EpiFusionBwdParams), ctypes.c_void_p]
     lib.epi_sample_locs_f32.restype = ctypes.c_int
     lib.epi_sample_locs_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_int32, ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_float,

@@ -29,7 +29,7 @@ bool src_is_channels_last(const EpiFusionParams *p) {
 
 struct Plan {
     size_t off_src = 0, off_prez = 0, off_counter = 0, off_ref = 0, off_order = 0, off_wplanes = 0, off_geom = 0, total = 0;
-    bool stage_src = false, has_z = false, tile = false, sector = false, pipe = false;
+    bool stage_src = false, has_z = false, tile = false, sector = false, pipe = false, unstage = false;
 };
 
 bool want_pipe(const EpiFusionParams *p) {
@@ -52,7 +52,9 @@ Plan make_plan(const EpiFusionParams *p) {
         pl.has_z = p->z_weight_folded != nullptr;
         size_t off = 0;
         pl.off_ref = off; off += align_up(2 * map);
-        if (pl.has_z) { pl.off_prez = off; off += align_up(map); }
+        // pre-z planes (z path) or the pixel-major fp32 plane the fused kernel writes when the caller's tensor is NCHW
+        pl.unstage = !pl.has_z && !(p->out_stride[1] == 1 && p->out_stride[3] % 4 == 0 && p->out_stride[2] % 4 == 0 && p->out_stride[0] % 4 == 0);
+        if (pl.has_z || pl.unstage) { pl.off_prez = off; off += align_up(map); }
         pl.off_counter = off; off += 256;
         if (pl.has_z && epi::zgemm_supported(p->C)) { pl.off_wplanes = off; off += align_up((size_t)p->C * p->C * 4); }
         if (!p->cache) {               // no persistent cache: pixel order and pair constants are rebuilt in the workspace every call
@@ -228,6 +230,11 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
         a.out_hi = reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_prez);
         a.out_lo = a.out_hi + (size_t)p->N * p->C * p->H * p->W;
         a.add_ref = 0;
+    } else if (pl.pipe && pl.unstage) {   // fused feature leaves the kernel pixel-major (full 128-byte lines); a transposition pass writes `out`
+        a.out = reinterpret_cast<float *>(ws + pl.off_prez);
+        a.out_stride[0] = (int64_t)p->C * p->H * p->W; a.out_stride[1] = 1;
+        a.out_stride[2] = (int64_t)p->W * p->C; a.out_stride[3] = p->C;
+        a.add_ref = 0;
     } else if (pl.has_z) {     // fused feature goes to the pre-z buffer (contiguous NCHW), epilogue writes `out`
         a.out = reinterpret_cast<float *>(ws + pl.off_prez);
         a.out_stride[0] = (int64_t)p->C * p->H * p->W; a.out_stride[1] = (int64_t)p->H * p->W;
@@ -251,6 +258,11 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
     if (g_timing) { cudaEventRecord(g_ev1, st); g_timing_valid = 1; }
     launches++;
 
+    if (pl.pipe && pl.unstage) {
+        e = epi::launch_unstage(a.out, p->add_ref_residual ? p->feat_ref : nullptr, p->ref_stride, p->out, p->out_stride, p->N, p->C, p->H, p->W, st);
+        if (e != cudaSuccess) return fail(EPI_ECUDA, "output transposition launch failed: %s", cudaGetErrorString(e));
+        launches++;
+    }
     if (z_tc) {
         epi::ZGemmArgs z;
         memset(&z, 0, sizeof(z));
@@ -272,6 +284,53 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
         z.z_residual = p->z_residual; z.add_ref = p->add_ref_residual;
         e = epi::launch_z_epilogue(z, st);
         if (e != cudaSuccess) return fail(EPI_ECUDA, "z epilogue launch failed: %s", cudaGetErrorString(e));
+        launches++;
+    }
+    g_launches = launches;
+    return EPI_OK;
+}
+
+size_t epi_fusion_backward_workspace_bytes(const EpiFusionBwdParams *p) {
+    if (!p || p->N <= 0 || p->C <= 0 || p->H <= 0 || p->W <= 0) return 0;
+    const size_t map = (size_t)p->N * p->C * p->H * p->W * sizeof(float);
+    return 2 * align_up(map);          // pixel-major copy of feat_src + pixel-major accumulator of its gradient
+}
+
+int epi_fusion_backward_f32(const EpiFusionBwdParams *p, void *stream) {
+    if (!p) return fail(EPI_EINVAL, "params is null");
+    if (!p->feat_ref || !p->feat_src || !p->attn || !p->grad_out) return fail(EPI_EINVAL, "feat_ref/feat_src/attn/grad_out must be non-null");
+    if (!p->sample_locs_in && (!p->P_ref || !p->P_src)) return fail(EPI_EINVAL, "P_ref/P_src required without sample_locs_in");
+    if (p->N <= 0 || p->C <= 0 || p->H < 2 || p->W < 2 || p->K < 2 || p->K > 256) return fail(EPI_EINVAL, "bad shape");
+    if (p->C > 512 || (p->C > 128 && p->C % 4 != 0)) return fail(EPI_EINVAL, "backward supports C <= 128, or C <= 512 with C % 4 == 0");
+    if (!p->grad_ref && !p->grad_src) return EPI_OK;
+    const size_t need = epi_fusion_backward_workspace_bytes(p);
+    if (!p->workspace || p->workspace_bytes < need) return fail(EPI_EWORKSPACE, "workspace too small");
+    if (reinterpret_cast<uintptr_t>(p->workspace) % 256 != 0) return fail(EPI_EINVAL, "workspace must be 256-byte aligned");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t map = (size_t)p->N * p->C * p->H * p->W * sizeof(float);
+    float *nhwc = reinterpret_cast<float *>(p->workspace);
+    float *dsrc = reinterpret_cast<float *>(static_cast<char *>(p->workspace) + align_up(map));
+    cudaError_t e = epi::launch_nchw_to_nhwc(p->feat_src, p->src_stride, nhwc, p->N, p->C, p->H, p->W, st);
+    if (e != cudaSuccess) return fail(EPI_ECUDA, "layout staging launch failed: %s", cudaGetErrorString(e));
+    int launches = 1;
+    if (p->grad_src) {
+        e = cudaMemsetAsync(dsrc, 0, map, st);
+        if (e != cudaSuccess) return fail(EPI_ECUDA, "memset failed: %s", cudaGetErrorString(e));
+    }
+    epi::BwdArgs a;
+    memset(&a, 0, sizeof(a));
+    a.feat_ref = p->feat_ref; a.src_nhwc = nhwc; a.P_ref = p->P_ref; a.P_src = p->P_src; a.locs_in = p->sample_locs_in;
+    a.attn = p->attn; a.grad_out = p->grad_out; a.grad_attn = p->grad_attn; a.grad_ref = p->grad_ref;
+    a.dsrc_nhwc = p->grad_src ? dsrc : nullptr;
+    for (int i = 0; i < 4; i++) { a.ref_stride[i] = p->ref_stride[i]; a.gout_stride[i] = p->gout_stride[i]; a.gref_stride[i] = p->gref_stride[i]; }
+    a.N = p->N; a.C = p->C; a.softmax_scale = p->softmax_scale; a.grad_keys = p->grad_keys; a.grad_vals = p->grad_vals;
+    a.geom = make_geom(p->H, p->W, p->K, p->downsample, p->img_scale, p->eps, p->correct_normalize, p->align_corners);
+    e = epi::launch_fusion_bwd(a, st);
+    if (e != cudaSuccess) return fail(EPI_ECUDA, "backward kernel launch failed: %s", cudaGetErrorString(e));
+    launches++;
+    if (p->grad_src) {
+        e = epi::launch_unstage(dsrc, nullptr, p->gsrc_stride, p->grad_src, p->gsrc_stride, p->N, p->C, p->H, p->W, st);
+        if (e != cudaSuccess) return fail(EPI_ECUDA, "gradient transposition launch failed: %s", cudaGetErrorString(e));
         launches++;
     }
     g_launches = launches;

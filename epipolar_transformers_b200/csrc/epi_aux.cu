@@ -109,6 +109,62 @@ cudaError_t launch_split_planes(const float *src, const int64_t stride[4], __nv_
 }
 
 // ------------------------------------------------------------------------------------------
+// Pixel-major fp32 plane [N,H*W,C] (what the fused kernel writes with full 128-byte lines) -> the caller's
+// [N,C,H,W] tensor (any strides), optionally adding the caller's residual feat_ref (resnet.py:388).  64 x 64
+// tiles through shared memory: float4 reads along channels, float4 writes along pixels.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unstage_kernel(const float *__restrict__ pm, const float *__restrict__ ref, int64_t rn,
+                                                      int64_t rc, int64_t rh, int64_t rw, float *__restrict__ out, int64_t on,
+                                                      int64_t oc, int64_t oh, int64_t ow, int C, int H, int W) {
+    __shared__ float tile[64][65];                              // [channel][pixel]
+    const int HW = H * W, t = threadIdx.x;
+    const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+    {
+        const int q = t & 15, pl = t >> 4;                      // 16 float4 per pixel row (64 channels), 16 pixels per pass
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int p = p0 + pl + i * 16, c = c0 + q * 4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < HW && c < C) v = __ldg(reinterpret_cast<const float4 *>(pm + ((size_t)n * HW + p) * C + c));   // C % 4 == 0
+            tile[q * 4 + 0][pl + i * 16] = v.x; tile[q * 4 + 1][pl + i * 16] = v.y;
+            tile[q * 4 + 2][pl + i * 16] = v.z; tile[q * 4 + 3][pl + i * 16] = v.w;
+        }
+    }
+    __syncthreads();
+    const bool vec_o = (ow == 1) && (oh == W) && (HW % 4 == 0) && (oc % 4 == 0) && (on % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const bool vec_r = !ref || ((rw == 1) && (rh == W) && (rc % 4 == 0) && (rn % 4 == 0) && ((reinterpret_cast<uintptr_t>(ref) & 15) == 0));
+    const int q = t & 15, cy = t >> 4;                          // 16 float4 per channel row, 16 channels per pass
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int c = c0 + cy + i * 16, p = p0 + q * 4;
+        if (c >= C || p >= HW) continue;
+        float v[4] = {tile[cy + i * 16][q * 4], tile[cy + i * 16][q * 4 + 1], tile[cy + i * 16][q * 4 + 2], tile[cy + i * 16][q * 4 + 3]};
+        if (vec_o && vec_r && p + 3 < HW) {
+            if (ref) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4 *>(ref + (int64_t)n * rn + (int64_t)c * rc + p));
+                v[0] += r4.x; v[1] += r4.y; v[2] += r4.z; v[3] += r4.w;
+            }
+            *reinterpret_cast<float4 *>(out + (int64_t)n * on + (int64_t)c * oc + p) = make_float4(v[0], v[1], v[2], v[3]);
+        } else {
+            for (int j = 0; j < 4 && p + j < HW; j++) {
+                const int y = (p + j) / W, x = (p + j) % W;
+                float o = v[j];
+                if (ref) o += __ldg(ref + (int64_t)n * rn + (int64_t)c * rc + (int64_t)y * rh + (int64_t)x * rw);
+                out[(int64_t)n * on + (int64_t)c * oc + (int64_t)y * oh + (int64_t)x * ow] = o;
+            }
+        }
+    }
+}
+
+cudaError_t launch_unstage(const float *pm, const float *ref, const int64_t ref_stride[4], float *out, const int64_t out_stride[4],
+                           int N, int C, int H, int W, cudaStream_t st) {
+    dim3 grid((H * W + 63) / 64, (C + 63) / 64, N);
+    unstage_kernel<<<grid, 256, 0, st>>>(pm, ref, ref ? ref_stride[0] : 0, ref ? ref_stride[1] : 0, ref ? ref_stride[2] : 0,
+                                         ref ? ref_stride[3] : 0, out, out_stride[0], out_stride[1], out_stride[2], out_stride[3], C, H, W);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
 // Fold conv1x1 z + eval BN (epipolar.py:250-251, BN.py:79 with training=False) into Wf, bf.
 // ------------------------------------------------------------------------------------------
 __global__ void fold_z_bn_kernel(const float *__restrict__ zw, const float *__restrict__ zb,

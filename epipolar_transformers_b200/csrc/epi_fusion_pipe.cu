@@ -235,6 +235,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                         const size_t off = ((size_t)d.n * HW + y * W + x) * C + c0;
                         *reinterpret_cast<uint2 *>(a.out_hi + off) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
                         *reinterpret_cast<uint2 *>(a.out_lo + off) = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+                    } else if (a.out_stride[1] == 1 && !a.add_ref) {
+                        // channel-contiguous output (channels_last, or the library's pixel-major plane): one 16-byte store per lane
+                        *reinterpret_cast<float4 *>(a.out + (int64_t)d.n * a.out_stride[0] + (int64_t)y * a.out_stride[2] + (int64_t)x * a.out_stride[3] + c0) = o;
                     } else {
                         const float ov[4] = {o.x, o.y, o.z, o.w};
                         float *ob = a.out + (int64_t)d.n * a.out_stride[0] + (int64_t)y * a.out_stride[2] + (int64_t)x * a.out_stride[3];

@@ -27,6 +27,23 @@ struct FusionArgs {
     GeomCfg geom;
 };
 
+// Backward of the fused attention (epi_fusion_bwd.cu)
+struct BwdArgs {
+    const float *feat_ref;  int64_t ref_stride[4];
+    const float *src_nhwc;                    // [N,H,W,C] contiguous fp32
+    const float *P_ref, *P_src, *locs_in;
+    const float *attn;                        // [N,K,H,W] saved by the forward
+    const float *grad_out;  int64_t gout_stride[4];
+    const float *grad_attn;                   // optional [N,K,H,W]
+    float *grad_ref;        int64_t gref_stride[4];   // optional
+    float *dsrc_nhwc;                         // optional [N,H,W,C] fp32, zero-initialised accumulator
+    int N, C;
+    float softmax_scale;
+    int grad_keys, grad_vals;
+    GeomCfg geom;
+};
+cudaError_t launch_fusion_bwd(const BwdArgs &a, cudaStream_t st);
+
 // z-projection epilogue:  y[n,o,p] = sum_c Wf[o,c]·x[n,c,p] + bf[o] (+x[n,o,p]) (+ref[n,o,p])
 struct ZArgs {
     const float *x;         int64_t x_stride[4];     // pre-z fused feature
@@ -67,6 +84,8 @@ cudaError_t launch_stage(const float *ref, const int64_t ref_stride[4], const fl
 
 cudaError_t launch_nchw_to_nhwc(const float *src, const int64_t stride[4], float *dst, int N, int C, int H, int W, cudaStream_t st);
 cudaError_t launch_z_epilogue(const ZArgs &z, cudaStream_t st);
+cudaError_t launch_unstage(const float *pm, const float *ref, const int64_t ref_stride[4], float *out, const int64_t out_stride[4],
+                           int N, int C, int H, int W, cudaStream_t st);
 cudaError_t launch_fold_z_bn(const float *zw, const float *zb, const float *g, const float *b, const float *mean,
                              const float *var, float eps, int C, float *wf, float *bf, cudaStream_t st);
 cudaError_t launch_sample_locs(const float *P_ref, const float *P_src, float *locs, int N, const GeomCfg &gc, cudaStream_t st);

@@ -145,6 +145,83 @@ def epipolar_fusion(feat_ref, feat_src, P_ref, P_src, *, K, downsample=4.0, img_
     return out, corr, attn, locs
 
 
+def epipolar_fusion_backward(feat_ref, feat_src, P_ref, P_src, attn, grad_out, *, K, downsample=4.0, img_scale=1.0,
+                             softmax_scale=0.125, correct_normalize=False, align_corners=False, grad_attn=None,
+                             sample_locs_in=None, grad_keys=True, grad_vals=True, need_ref=True, need_src=True):
+    """Backward of `epipolar_fusion` without the z epilogue: returns (dL/dfeat_ref | None, dL/dfeat_src | None).
+    Restates autograd through epipolar.py:188-247 (grid_sample x2, mul/sum, ==0 mask, softmax, weighted sum);
+    grad_keys / grad_vals = 'other1' / 'other2' in cfg.EPIPOLAR.OTHER_GRAD (:141-153)."""
+    lib = _lib.load()
+    N, C, H, W = feat_ref.shape
+    dev = feat_ref.device
+    grad_out = grad_out if grad_out.dtype == torch.float32 else grad_out.float()
+    attn = attn.contiguous()
+    g_ref = torch.empty_like(feat_ref) if need_ref else None
+    g_src = torch.empty_like(feat_src) if need_src else None
+    if not need_ref and not need_src:
+        return None, None
+    p = _lib.EpiFusionBwdParams()
+    p.feat_ref = feat_ref.data_ptr(); p.ref_stride = _strides4(feat_ref)
+    p.feat_src = feat_src.data_ptr(); p.src_stride = _strides4(feat_src)
+    if sample_locs_in is None:
+        P_ref = P_ref.to(device=dev, dtype=torch.float32).contiguous(); P_src = P_src.to(device=dev, dtype=torch.float32).contiguous()
+        p.P_ref = P_ref.data_ptr(); p.P_src = P_src.data_ptr()
+    else:
+        sample_locs_in = sample_locs_in.to(device=dev, dtype=torch.float32).contiguous()
+        p.sample_locs_in = sample_locs_in.data_ptr()
+    p.attn = attn.data_ptr()
+    p.grad_out = grad_out.data_ptr(); p.gout_stride = _strides4(grad_out)
+    if grad_attn is not None:
+        grad_attn = grad_attn.to(dtype=torch.float32).contiguous()
+        p.grad_attn = grad_attn.data_ptr()
+    if g_ref is not None:
+        p.grad_ref = g_ref.data_ptr(); p.gref_stride = _strides4(g_ref)
+    if g_src is not None:
+        p.grad_src = g_src.data_ptr(); p.gsrc_stride = _strides4(g_src)
+    p.N, p.C, p.H, p.W, p.K = N, C, H, W, int(K)
+    p.downsample = float(downsample); p.img_scale = float(img_scale); p.eps = _EPSILON; p.softmax_scale = float(softmax_scale)
+    p.align_corners = int(bool(align_corners)); p.correct_normalize = int(bool(correct_normalize))
+    p.grad_keys = int(bool(grad_keys)); p.grad_vals = int(bool(grad_vals))
+    nbytes = lib.epi_fusion_backward_workspace_bytes(ctypes.byref(p))
+    ws = torch.empty(max(nbytes, 1), device=dev, dtype=torch.uint8)
+    p.workspace = ws.data_ptr(); p.workspace_bytes = nbytes
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.epi_fusion_backward_f32(ctypes.byref(p), ctypes.c_void_p(stream)), "epi_fusion_backward_f32")
+    return g_ref, g_src
+
+
+class _FusionFn(torch.autograd.Function):
+    """The fused attention under autograd (no z epilogue: conv/BN stay in PyTorch when gradients are needed)."""
+
+    @staticmethod
+    def forward(ctx, feat_ref, feat_src, P_ref, P_src, opts):
+        with torch.no_grad():
+            out, corr, attn, locs = epipolar_fusion(feat_ref, feat_src, P_ref, P_src, want_attn=True, **opts["fwd"])
+        ctx.save_for_backward(feat_ref, feat_src, P_ref, P_src, attn)
+        ctx.opts = opts
+        nd = [t for t in (corr, locs) if t is not None]
+        if nd:
+            ctx.mark_non_differentiable(*nd)
+        return out, corr, attn, locs
+
+    @staticmethod
+    def backward(ctx, g_out, g_corr, g_attn, g_locs):
+        feat_ref, feat_src, P_ref, P_src, attn = ctx.saved_tensors
+        o = ctx.opts
+        if g_out is None:
+            g_out = torch.zeros_like(feat_ref)
+        need_ref, need_src = ctx.needs_input_grad[0], ctx.needs_input_grad[1] and (o["grad_keys"] or o["grad_vals"])
+        f = o["fwd"]
+        g_ref, g_src = epipolar_fusion_backward(
+            feat_ref, feat_src, P_ref, P_src, attn, g_out, K=f["K"], downsample=f["downsample"], img_scale=f["img_scale"],
+            softmax_scale=f["softmax_scale"], correct_normalize=f["correct_normalize"], align_corners=f["align_corners"],
+            grad_attn=g_attn, grad_keys=o["grad_keys"], grad_vals=o["grad_vals"], need_ref=need_ref, need_src=need_src)
+        if ctx.needs_input_grad[1] and g_src is None:
+            g_src = torch.zeros_like(feat_src)
+        return g_ref, g_src, None, None, None
+
+
 def fold_z_bn(z: nn.Conv2d, bn: nn.BatchNorm2d):
     """(Wf, bf) such that BN_eval(z(x)) == Wf·x + bf, computed on the device (no host sync)."""
     lib = _lib.load()
@@ -256,21 +333,31 @@ class Epipolar(nn.Module):
             raise NotImplementedError("depth pass-through (epipolar.py:215-216) is not on the accelerated path")
         cfg = self.cfg
         ep = cfg.EPIPOLAR
-        if torch.is_grad_enabled() and (feat1.requires_grad or feat2.requires_grad):
-            raise NotImplementedError("backward of the fused op is not implemented yet (SURVEY.md 8f rank 1); "
-                                      "call under torch.no_grad()")
+        needs_grad = torch.is_grad_enabled() and (feat1.requires_grad or feat2.requires_grad)
         has_z = "z" in ep.PARAMETERIZED
-        fold = has_z and not self.training
+        fold = has_z and not self.training and not needs_grad
         want_locs = bool(cfg.VIS.EPIPOLAR_LINE)
-        out, corr, attn, locs = epipolar_fusion(
-            feat1, feat2, P1, P2, K=self.sample_size, downsample=self.downsample,
-            img_scale=cfg.DATASETS.IMAGE_RESIZE * cfg.DATASETS.PREDICT_RESIZE,
-            softmax_scale=ep.SOFTMAXSCALE, correct_normalize=ep.USE_CORRECT_NORMALIZE,
-            align_corners=self.align_corners, z_folded=self._folded() if fold else None,
-            z_residual=bool(ep.ZRESIDUAL) if fold else False,
-            add_ref_residual=self.fuse_ref_residual and (fold or not has_z),
-            want_attn=self.emit_attn, want_corr=self.emit_corr, want_locs=want_locs, variant=self.variant,
-            state=self._state_for(feat1))
+        if needs_grad:
+            # training: the fused attention runs under autograd (CUDA backward kernel); z conv + BN stay in PyTorch
+            opts = dict(fwd=dict(K=self.sample_size, downsample=self.downsample,
+                                 img_scale=cfg.DATASETS.IMAGE_RESIZE * cfg.DATASETS.PREDICT_RESIZE,
+                                 softmax_scale=ep.SOFTMAXSCALE, correct_normalize=ep.USE_CORRECT_NORMALIZE,
+                                 align_corners=self.align_corners, want_corr=self.emit_corr, want_locs=want_locs,
+                                 variant=self.variant),
+                        grad_keys="other1" in ep.OTHER_GRAD, grad_vals="other2" in ep.OTHER_GRAD)
+            out, corr, attn, locs = _FusionFn.apply(feat1, feat2, P1, P2, opts)
+            if not self.emit_attn:
+                attn = None
+        else:
+            out, corr, attn, locs = epipolar_fusion(
+                feat1, feat2, P1, P2, K=self.sample_size, downsample=self.downsample,
+                img_scale=cfg.DATASETS.IMAGE_RESIZE * cfg.DATASETS.PREDICT_RESIZE,
+                softmax_scale=ep.SOFTMAXSCALE, correct_normalize=ep.USE_CORRECT_NORMALIZE,
+                align_corners=self.align_corners, z_folded=self._folded() if fold else None,
+                z_residual=bool(ep.ZRESIDUAL) if fold else False,
+                add_ref_residual=self.fuse_ref_residual and (fold or not has_z),
+                want_attn=self.emit_attn, want_corr=self.emit_corr, want_locs=want_locs, variant=self.variant,
+                state=self._state_for(feat1))
         if has_z and not fold:
             # training-mode BN needs batch statistics (+ autograd to z/bn): keep conv/BN in PyTorch
             finalout = self.bn(self.z(out))
@@ -278,6 +365,8 @@ class Epipolar(nn.Module):
                 finalout = finalout + out
             if self.fuse_ref_residual:
                 finalout = finalout + feat1
+        elif needs_grad and self.fuse_ref_residual:
+            finalout = out + feat1
         else:
             finalout = out
         return finalout, corr, attn, (locs.transpose(0, 1) if want_locs else None)

@@ -101,6 +101,38 @@ size_t epi_fusion_cache_bytes(const EpiFusionParams *p);
  * Asynchronous on `stream` (a cudaStream_t); returns launch-time errors only. */
 int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream);
 
+/* ---- backward of the fused attention --------------------------------------------------------
+ * Replaces autograd through  F.grid_sample x2 / mul / sum / softmax  of /root/reference/modeling/layers/epipolar.py:188-247
+ * (called under autograd by /root/reference/engine/trainer.py:72).  Sample locations are constants (:178 torch.no_grad).
+ * grad_keys / grad_vals select the OTHER_GRAD members 'other1' / 'other2' (:141-153).  The z conv + BN of training mode
+ * stay in PyTorch, so `grad_out` is the gradient w.r.t. the PRE-z fused feature. */
+typedef struct EpiFusionBwdParams {
+    const float *feat_ref;        /* [N,C,H,W] logical, strides below */
+    int64_t ref_stride[4];
+    const float *feat_src;
+    int64_t src_stride[4];
+    const float *P_ref, *P_src;   /* [N,3,4] */
+    const float *sample_locs_in;  /* optional, as in the forward */
+    const float *attn;            /* [N,K,H,W] contiguous: the forward's attention output */
+    const float *grad_out;        /* [N,C,H,W] logical: dL/d(fused feature) */
+    int64_t gout_stride[4];
+    const float *grad_attn;       /* optional [N,K,H,W] contiguous: dL/d(attention output) */
+    float *grad_ref;              /* optional out [N,C,H,W] logical: dL/dfeat_ref */
+    int64_t gref_stride[4];
+    float *grad_src;              /* optional out [N,C,H,W] logical: dL/dfeat_src (overwritten, not accumulated) */
+    int64_t gsrc_stride[4];
+    void *workspace;
+    size_t workspace_bytes;       /* >= epi_fusion_backward_workspace_bytes(p) */
+    int32_t N, C, H, W, K;
+    float downsample, img_scale, eps, softmax_scale;
+    int32_t align_corners, correct_normalize;
+    int32_t grad_keys, grad_vals; /* 'other1' / 'other2' in cfg.EPIPOLAR.OTHER_GRAD */
+    int32_t reserved[4];
+} EpiFusionBwdParams;
+
+size_t epi_fusion_backward_workspace_bytes(const EpiFusionBwdParams *p);
+int epi_fusion_backward_f32(const EpiFusionBwdParams *p, void *stream);
+
 /* Only the geometry: sample locations [K,N,H,W,2] for (P_ref,P_src)  (grid2sample_locs). */
 int epi_sample_locs_f32(const float *P_ref, const float *P_src, float *sample_locs_out, int32_t N,
                         int32_t H, int32_t W, int32_t K, float downsample, float img_scale, float eps,

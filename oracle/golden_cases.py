@@ -43,6 +43,8 @@ CASES = {
 }
 
 SUBSAMPLE = 48     # pixels per item frozen for the big cases
+DENSE = 1024       # pixels per item of the dense fixtures (<case>_dense.npz) of the BASELINE-sized cases below
+DENSE_CASES = ("cfg2_r50_256_randn", "cfg3_r152_384")
 
 
 def case_cfg(spec):
@@ -89,3 +91,15 @@ def subsample_pixels(name):
     ys = rng.integers(0, spec["H"], size=(spec["N"], SUBSAMPLE))
     xs = rng.integers(0, spec["W"], size=(spec["N"], SUBSAMPLE))
     return np.stack([ys, xs], -1)
+
+
+def dense_pixels(name):
+    """Deterministic [N, DENSE, 2] (y, x) picks WITHOUT repetition for the dense fixtures."""
+    spec = CASES[name]
+    rng = np.random.default_rng(case_seed(name) + 11)
+    out = np.zeros((spec["N"], DENSE, 2), dtype=np.int64)
+    for n in range(spec["N"]):
+        flat = rng.choice(spec["H"] * spec["W"], size=DENSE, replace=False)
+        out[n, :, 0] = flat // spec["W"]
+        out[n, :, 1] = flat % spec["W"]
+    return out

@@ -62,6 +62,17 @@ def main(names=None):
         path = os.path.join(out_dir, name + ".npz")
         np.savez_compressed(path, **rec)
         print("%-22s %8.1f KB  out|max|=%.4g" % (name, os.path.getsize(path) / 1024, np.abs(r["out"]).max()))
+        if name in gc.DENSE_CASES:                              # 1024 pixels per item: T1/T3 at BASELINE shapes with real coverage
+            px = gc.dense_pixels(name)
+            n_idx = np.arange(spec["N"])[:, None]
+            yy, xx = px[..., 0], px[..., 1]
+            dense = dict(meta=rec["meta"], pixels=px, out=r["out"][n_idx, :, yy, xx], attn=r["attn"][n_idx, :, yy, xx],
+                         corr_pos=r["corr_pos"][n_idx, yy, xx],
+                         sample_locs=r["sample_locs"].transpose(1, 2, 3, 0, 4)[n_idx, yy, xx],
+                         out_absmax=np.float64(np.abs(r["out"]).max()))
+            path = os.path.join(out_dir, name + "_dense.npz")
+            np.savez_compressed(path, **dense)
+            print("%-22s %8.1f KB  (dense)" % (name, os.path.getsize(path) / 1024))
 
 
 if __name__ == "__main__":

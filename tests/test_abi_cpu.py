@@ -70,15 +70,19 @@ def test_workspace_plan(lib):
     buf = (ctypes.c_float * 4)()
     p.feat_src = ctypes.addressof(buf)
     p.src_stride = (ctypes.c_int64 * 4)(256 * 4096, 4096, 64, 1)           # NCHW: needs staging
+    p.out_stride = (ctypes.c_int64 * 4)(256 * 4096, 4096, 64, 1)           # NCHW output: pixel-major plane + transposition pass
     m = 4 * 256 * 64 * 64 * 4
     order = 4 * 4096 * 2                                                     # pixel order list (u16)
     geom = 256                                                               # 4 pairs x 44 B of pair constants, 256-B granules
     pipe = 2 * m + 256 + order + geom           # ref + src bf16 (hi, lo) planes, counter/error words, pixel order, pair constants
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == pipe + m      # + the pixel-major fp32 output plane
+    p.out_stride = (ctypes.c_int64 * 4)(256 * 4096, 1, 64 * 256, 256)      # channels_last output: written directly
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == pipe
     assert lib.epi_fusion_cache_bytes(ctypes.byref(p)) == 4 * 32 * 4 + geom + order      # keys + pair constants + order
     p.cache = ctypes.addressof(buf)                                          # with a persistent cache they leave the workspace
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 2 * m + 256
     p.cache = None
+    p.out_stride = (ctypes.c_int64 * 4)(256 * 4096, 4096, 64, 1)
     p.z_weight_folded = ctypes.addressof(buf)
     wpl = 256 * 256 * 4                                                      # folded z weight as bf16 (hi, lo) planes
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == pipe + m + wpl    # + pre-z bf16 planes + weight planes
