@@ -17,7 +17,7 @@ VARIANTS = {"auto": EPI_VARIANT_AUTO, "warp": EPI_VARIANT_WARP, "tile": EPI_VARI
             "pipe": EPI_VARIANT_PIPE}
 
 EXPORTS = ("epi_version", "epi_last_error", "epi_fusion_workspace_bytes", "epi_fusion_cache_bytes", "epi_fusion_forward_f32",
-           "epi_fusion_backward_workspace_bytes", "epi_fusion_backward_f32",
+           "epi_fusion_backward_workspace_bytes", "epi_fusion_backward_f32", "epi_find_peaks_f32",
            "epi_sample_locs_f32", "epi_fold_z_bn_f32", "epi_last_launch_count", "epi_umma_selftest",
            "epi_kernel_timing_enable", "epi_kernel_timing_last_ms")
 
@@ -90,6 +90,9 @@ def load():
     lib.epi_fusion_backward_workspace_bytes.argtypes = [ctypes.POINTER(EpiFusionBwdParams)]
     lib.epi_fusion_backward_f32.restype = ctypes.c_int
     lib.epi_fusion_backward_f32.argtypes = [ctypes.POINTER(EpiFusionBwdParams), ctypes.c_void_p]
+    lib.epi_find_peaks_f32.restype = ctypes.c_int
+    lib.epi_find_peaks_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_int32, ctypes.c_void_p]
     lib.epi_sample_locs_f32.restype = ctypes.c_int
     lib.epi_sample_locs_f32.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32,
                                         ctypes.c_int32, ctypes.c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_float,

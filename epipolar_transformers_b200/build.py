@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libepipolar_b200.so")
-SOURCES = ["epi_abi.cu", "epi_aux.cu", "epi_fusion_warp.cu", "epi_fusion_tile.cu", "epi_fusion_pipe.cu", "epi_fusion_bwd.cu", "epi_stage.cu", "epi_zgemm.cu", "epi_umma_selftest.cu"]
+SOURCES = ["epi_abi.cu", "epi_aux.cu", "epi_fusion_warp.cu", "epi_fusion_tile.cu", "epi_fusion_pipe.cu", "epi_fusion_bwd.cu", "epi_stage.cu", "epi_peaks.cu", "epi_zgemm.cu", "epi_umma_selftest.cu"]
 HEADERS = ["epi_common.cuh", "epi_kernels.cuh", "epi_umma.cuh", os.path.join("..", "..", "include", "epipolar_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]

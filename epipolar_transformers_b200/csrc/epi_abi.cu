@@ -348,6 +348,17 @@ int epi_sample_locs_f32(const float *P_ref, const float *P_src, float *sample_lo
     return EPI_OK;
 }
 
+int epi_find_peaks_f32(const float *heatmaps, float *locs, float *scores, int32_t B, int32_t J, int32_t H, int32_t W,
+                       float radius, float downsample, float threshold, int32_t int_div, void *stream) {
+    if (!heatmaps || !locs || !scores) return fail(EPI_EINVAL, "null pointer");
+    if (B <= 0 || J <= 0 || H < 2 || W < 2 || !(radius > 0.f)) return fail(EPI_EINVAL, "bad shape or radius");
+    if ((int)(radius + 0.5f) < 1) return fail(EPI_EINVAL, "radius must round to at least 1");
+    cudaError_t e = epi::launch_peaks(heatmaps, locs, scores, B, J, H, W, radius, downsample, threshold, int_div,
+                                      reinterpret_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail(EPI_ECUDA, "peak kernel launch failed: %s", cudaGetErrorString(e));
+    return EPI_OK;
+}
+
 int epi_fold_z_bn_f32(const float *z_weight, const float *z_bias, const float *bn_weight, const float *bn_bias,
                       const float *bn_mean, const float *bn_var, float bn_eps, int32_t C, float *w_folded,
                       float *b_folded, void *stream) {

@@ -88,6 +88,8 @@ cudaError_t launch_unstage(const float *pm, const float *ref, const int64_t ref_
                            int N, int C, int H, int W, cudaStream_t st);
 cudaError_t launch_fold_z_bn(const float *zw, const float *zb, const float *g, const float *b, const float *mean,
                              const float *var, float eps, int C, float *wf, float *bf, cudaStream_t st);
+cudaError_t launch_peaks(const float *heat, float *locs, float *scores, int B, int J, int H, int W, float radius, float downsample,
+                         float threshold, int int_div, cudaStream_t st);
 cudaError_t launch_sample_locs(const float *P_ref, const float *P_src, float *locs, int N, const GeomCfg &gc, cudaStream_t st);
 
 }  // namespace epi

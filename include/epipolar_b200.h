@@ -138,6 +138,14 @@ int epi_sample_locs_f32(const float *P_ref, const float *P_src, float *sample_lo
                         int32_t H, int32_t W, int32_t K, float downsample, float img_scale, float eps,
                         int32_t correct_normalize, void *stream);
 
+/* find_tensor_peak_batch for a whole batch (replaces the per-item Python loop at
+ * /root/reference/modeling/backbones/resnet.py:423-428 over modeling/backbones/basic_batch.py:17-63):
+ * heatmaps [B,J,H,W] contiguous -> locs [B,J,2] (x, y in image coordinates, pix2coord applied) and scores [B,J].
+ * radius = cfg.KEYPOINT.SIGMA; threshold 1e-6 in the reference; int_div = 1 reproduces torch < 1.4's integer `index / W`,
+ * 0 the true division of current torch (what the reference computes under the torch installed with this library). */
+int epi_find_peaks_f32(const float *heatmaps, float *locs, float *scores, int32_t B, int32_t J, int32_t H, int32_t W,
+                       float radius, float downsample, float threshold, int32_t int_div, void *stream);
+
 /* Fold conv1x1 z + eval BatchNorm into (Wf, bf) on the device, no host sync:
  *   Wf[o,c] = s[o]·Wz[o,c],  bf[o] = s[o]·(bz[o] − mean[o]) + beta[o],  s = gamma/sqrt(var+bn_eps). */
 int epi_fold_z_bn_f32(const float *z_weight, const float *z_bias, const float *bn_weight,
