@@ -19,7 +19,7 @@ VARIANTS = {"auto": EPI_VARIANT_AUTO, "warp": EPI_VARIANT_WARP, "tile": EPI_VARI
 EXPORTS = ("epi_version", "epi_last_error", "epi_fusion_workspace_bytes", "epi_fusion_cache_bytes", "epi_fusion_forward_f32",
            "epi_fusion_backward_workspace_bytes", "epi_fusion_backward_f32", "epi_find_peaks_f32",
            "epi_sample_locs_f32", "epi_fold_z_bn_f32", "epi_last_launch_count", "epi_umma_selftest",
-           "epi_kernel_timing_enable", "epi_kernel_timing_last_ms")
+           "epi_kernel_timing_enable", "epi_kernel_timing_last_ms", "epi_kernel_timing_last3")
 
 _fp = ctypes.POINTER(ctypes.c_float)
 
@@ -106,6 +106,8 @@ def load():
     lib.epi_kernel_timing_enable.restype = ctypes.c_int
     lib.epi_kernel_timing_enable.argtypes = [ctypes.c_int]
     lib.epi_kernel_timing_last_ms.restype = ctypes.c_float
+    lib.epi_kernel_timing_last3.restype = ctypes.c_int
+    lib.epi_kernel_timing_last3.argtypes = [ctypes.POINTER(ctypes.c_float)]
     v = lib.epi_version()
     if v != EPI_ABI_VERSION:
         raise RuntimeError("libepipolar_b200.so ABI version %d != expected %d" % (v, EPI_ABI_VERSION))

@@ -11,7 +11,7 @@ namespace {
 thread_local char g_err[512] = "";
 thread_local int g_launches = 0;
 thread_local int g_timing = 0, g_timing_valid = 0;
-thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+thread_local cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr, g_evA = nullptr, g_evB = nullptr;   // A: call start, B: call end
 
 int fail(int code, const char *fmt, const char *detail = "") {
     snprintf(g_err, sizeof(g_err), fmt, detail);
@@ -123,6 +123,17 @@ int epi_last_launch_count(void) { return g_launches; }
 
 int epi_kernel_timing_enable(int on) { g_timing = on ? 1 : 0; return EPI_OK; }
 
+int epi_kernel_timing_last3(float *ms3) {
+    if (!ms3) return fail(EPI_EINVAL, "null pointer");
+    ms3[0] = ms3[1] = ms3[2] = -1.f;
+    if (!g_timing_valid || !g_ev0) return EPI_OK;
+    if (cudaEventSynchronize(g_evB) != cudaSuccess) return fail(EPI_ECUDA, "event synchronize failed");
+    cudaEventElapsedTime(&ms3[0], g_evA, g_ev0);      // operand staging (+ pixel order)
+    cudaEventElapsedTime(&ms3[1], g_ev0, g_ev1);      // fused attention kernel
+    cudaEventElapsedTime(&ms3[2], g_ev1, g_evB);      // epilogue pass (z GEMM / output transposition), 0 when there is none
+    return EPI_OK;
+}
+
 float epi_kernel_timing_last_ms(void) {
     if (!g_timing_valid || !g_ev0) return -1.f;
     float ms = -1.f;
@@ -152,6 +163,11 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
     int launches = 0;
     cudaError_t e;
     const __nv_bfloat16 *w_hi = nullptr, *w_lo = nullptr;
+    g_timing_valid = 0;
+    if (g_timing) {
+        if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); cudaEventCreate(&g_evA); cudaEventCreate(&g_evB); }
+        cudaEventRecord(g_evA, st);
+    }
 
     epi::FusionArgs a;
     memset(&a, 0, sizeof(a));
@@ -248,14 +264,10 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
 
     const bool use_tile = pl.tile && epi::fusion_tile_supported(a);
     if (pl.tile && !use_tile) return fail(EPI_EINVAL, "internal: tile plan without tile support");
-    g_timing_valid = 0;
-    if (g_timing) {
-        if (!g_ev0) { cudaEventCreate(&g_ev0); cudaEventCreate(&g_ev1); }
-        cudaEventRecord(g_ev0, st);
-    }
+    if (g_timing) cudaEventRecord(g_ev0, st);
     e = pl.pipe ? epi::launch_fusion_pipe(a, st) : (use_tile ? epi::launch_fusion_tile(a, st) : epi::launch_fusion_warp(a, st));
     if (e != cudaSuccess) return fail(EPI_ECUDA, "fusion kernel launch failed: %s", cudaGetErrorString(e));
-    if (g_timing) { cudaEventRecord(g_ev1, st); g_timing_valid = 1; }
+    if (g_timing) cudaEventRecord(g_ev1, st);
     launches++;
 
     if (pl.pipe && pl.unstage) {
@@ -286,6 +298,7 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
         if (e != cudaSuccess) return fail(EPI_ECUDA, "z epilogue launch failed: %s", cudaGetErrorString(e));
         launches++;
     }
+    if (g_timing) { cudaEventRecord(g_evB, st); g_timing_valid = 1; }
     g_launches = launches;
     return EPI_OK;
 }

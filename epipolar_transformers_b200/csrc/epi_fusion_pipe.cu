@@ -153,6 +153,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
     const int C = a.C, K = a.geom.K, H = a.geom.H, W = a.geom.W, HW = H * W;
     const int tiles_per_item = (HW + P - 1) / P;
     const int total_tiles = a.N * tiles_per_item;
+    // tail balancing: the tiles of the last, partial round over the grid are handed out as half items (16 pixels)
+    const int tail_tiles = a.tile_counter ? total_tiles % (int)gridDim.x : 0;
+    const int r_half = min(tiles_per_item, (tail_tiles + a.N - 1) / a.N);          // per pair
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwords = (HW + 31) >> 5;
     const int NH = (C + 127) >> 7;                  // channel halves of 128 (GEMM2 M)
@@ -476,16 +479,24 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 // ---- next group: pop the split stack or claim a new tile ----
                 if (st == 0) {
                     if (ct.sp == 0) {
-                        int tile;
-                        if (claimed == 0) tile = (int)blockIdx.x;
-                        else tile = a.tile_counter ? (int)gridDim.x + atomicAdd(a.tile_counter, 1) : (int)blockIdx.x + claimed * (int)gridDim.x;
+                        int c;
+                        if (claimed == 0) c = (int)blockIdx.x;
+                        else c = a.tile_counter ? (int)gridDim.x + atomicAdd(a.tile_counter, 1) : (int)blockIdx.x + claimed * (int)gridDim.x;
                         claimed++;
-                        if (tile < total_tiles) { ct.cur_tile = tile; ct.stack[0] = 0 | (P << 8); ct.sp = 1; }
-                        else ct.done = 1;
+                        // per pair: tiles [0, tpi - r_half) are claimed whole, the last r_half tiles as two halves each (the same
+                        // tiles of every pair, so results do not depend on a pair's position in the batch)
+                        const int whole = tiles_per_item - r_half;
+                        if (c < a.N * whole) { ct.cur_tile = (c / whole) * tiles_per_item + c % whole; ct.stack[0] = 0 | (P << 8); ct.sp = 1; }
+                        else if (c < a.N * whole + 2 * a.N * r_half) {
+                            const int h = c - a.N * whole, hh = h >> 1;
+                            ct.cur_tile = (hh / r_half) * tiles_per_item + whole + hh % r_half;
+                            ct.stack[0] = ((h & 1) * (P / 2)) | ((P / 2) << 8); ct.sp = 1;
+                        } else ct.done = 1;
                     }
                     if (!ct.done) ct.cur = ct.stack[--ct.sp];
                 }
                 named_bar(2, NSETUP);
+                PT(28);
                 if (ct.done) { done = true; break; }
                 const int tile = ct.cur_tile, g0 = ct.cur & 0xff, gn = ct.cur >> 8;
                 const int n = tile / tiles_per_item, trem = tile % tiles_per_item;
@@ -508,6 +519,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 } else if (st == P) { d.tile = tile; d.n = n; d.g0 = g0; d.gn = gn; }
                 for (int w = st - 64; w >= 0 && w < nwords; w += 64) d.bitmap[w] = 0u;     // warps 2,3 clear the bitmap
                 named_bar(2, NSETUP);
+                PT(29);
                 // ---- union of the in-bounds taps: lane <-> sample (consecutive samples fall into different words) ----
                 for (int i = g0 + sw; i < g0 + gn; i += NSETUP / 32) {
                     const uint32_t p = d.pix[i];
@@ -530,6 +542,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     }
                 }
                 named_bar(2, NSETUP);
+                PT(30);
                 // ---- exclusive prefix of popcounts (first setup warp; 16 words per lane max) ----
                 if (sw == 0) {
                     const int per = (nwords + 31) >> 5;
@@ -546,6 +559,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     if (lane == 31) ct.total = incl;
                 }
                 named_bar(2, NSETUP);
+                PT(31);
                 const int D = ct.total;
                 if (D > DMAX && gn > 1) {                 // split the group
                     if (st == 0) {
@@ -566,9 +580,11 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                         while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; d.idx[r++] = (uint16_t)(w * 32 + b); }
                     }
                 named_bar(2, NSETUP);
+                PT(17);
                 if (st < 16 && Dc > 0) { const int r = Dc + st; if (r < ((Dc + 15) & ~15)) d.idx[r] = d.idx[0]; }
                 if (st == 16) d.D = Dc;
                 named_bar(2, NSETUP);
+                PT(18);
                 break;
             }
             if (done) {

@@ -65,7 +65,8 @@ struct StageArgs {
     GeomCfg gc;
 };
 
-__global__ void __launch_bounds__(stg::NT) epi_stage_kernel(const StageArgs s) {
+// (min 5 blocks per SM: the layout-staging blocks need few registers; the rare order blocks may spill a little)
+__global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s) {
     using namespace stg;
     extern __shared__ __align__(16) uint8_t dyn[];        // transposition tile [64][65] fp32 | order blocks: histogram + pixel list
     float (*tile)[65] = reinterpret_cast<float (*)[65]>(dyn);
@@ -346,7 +347,7 @@ cudaError_t launch_stage(const float *ref, const int64_t ref_stride[4], const fl
     size_t smem = 64 * 65 * sizeof(float);
     if (s.do_order && (size_t)stg::NBIN * 4 + (size_t)H * W * 2 > smem) smem = (size_t)stg::NBIN * 4 + (size_t)H * W * 2;
     static thread_local size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
+    if (smem + 1024 > 48 * 1024 && smem > smem_set) {        // (+ the kernel's small static arrays)
         cudaError_t e = cudaFuncSetAttribute(epi_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         smem_set = smem;

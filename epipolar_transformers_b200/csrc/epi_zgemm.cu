@@ -22,7 +22,7 @@ namespace epi {
 using namespace umma;
 
 namespace zg {
-constexpr int NT = 256;
+constexpr int NT = 512;
 constexpr uint32_t A_PLANE = 16384;                 // 128 rows x 128 B
 constexpr uint32_t B_PLANE = 32768;                 // 256 rows x 128 B
 constexpr uint32_t STAGE = 2 * A_PLANE + 2 * B_PLANE;   // 96 KB
@@ -104,39 +104,70 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
     for (uint32_t it = 0; !mbar_try_wait(&bars[4], 0); ++it) if (it > (1u << 24)) __trap();
     tc_fence_after();
 
-    // epilogue: thread <-> pixel (TMEM lane), 32 output channels at a time
+    // ---- epilogue ------------------------------------------------------------------------------------------------
+    // phase 1 (thread <-> pixel = TMEM lane, 16 warps = 4 lane quadrants x 4 channel groups): accumulator + bias (+ ZRESIDUAL, read
+    //   from the pixel-major bf16 planes as 16-byte chunks) -> shared tile [channel][128 pixels] (the operand stages are free now);
+    // phase 2 (warp <-> channel row, lane <-> 4 consecutive pixels): + caller residual, 512-byte row segments of the NCHW output
+    //   per warp instruction.  Falls back to per-element addressing for strides that are not pixel-contiguous.
+    float *otile = reinterpret_cast<float *>(smem);            // [C][132] fp32 <= 256 * 132 * 4 = 135168 B of the 196608 B stage area
+    constexpr int OT = 132;
     {
         const int r = (warp & 3) * 32 + lane, p = p0 + r;
         const bool ok = p < HW;
-        const int py = ok ? p / W : 0, px = ok ? p % W : 0;
-        float *yb = z.y + (int64_t)n * z.y_stride[0] + (int64_t)py * z.y_stride[2] + (int64_t)px * z.y_stride[3];
-        const float *rb = z.ref ? z.ref + (int64_t)n * z.ref_stride[0] + (int64_t)py * z.ref_stride[2] + (int64_t)px * z.ref_stride[3] : nullptr;
-        for (int cb = (warp >> 2) * 32; cb < C; cb += 64) {
+        for (int cb = (warp >> 2) * 32; cb < C; cb += 128) {
             float v[32];
             tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + cb, v);
+            uint4 xh4[4], xl4[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) { xh4[u] = make_uint4(0, 0, 0, 0); xl4[u] = make_uint4(0, 0, 0, 0); }
+            if (ok && z.z_residual) {
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (cb + u * 8 < C) {
+                        xh4[u] = __ldg(reinterpret_cast<const uint4 *>(xh + (size_t)p * C + cb + u * 8));
+                        xl4[u] = __ldg(reinterpret_cast<const uint4 *>(xl + (size_t)p * C + cb + u * 8));
+                    }
+            }
             tmem_ld_wait();
-            if (ok) {
-                uint4 xh4[4], xl4[4];
-                if (z.z_residual) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        xh4[u] = (cb + u * 8 < C) ? __ldg(reinterpret_cast<const uint4 *>(xh + (size_t)p * C + cb + u * 8)) : make_uint4(0, 0, 0, 0);
-                        xl4[u] = (cb + u * 8 < C) ? __ldg(reinterpret_cast<const uint4 *>(xl + (size_t)p * C + cb + u * 8)) : make_uint4(0, 0, 0, 0);
+            for (int jj = 0; jj < 32; jj++) {
+                const int o = cb + jj;
+                if (o < C) {
+                    float y = v[jj] + __ldg(z.bf + o);
+                    if (z.z_residual) {
+                        const uint32_t wh = reinterpret_cast<const uint32_t *>(xh4)[jj >> 1], wl = reinterpret_cast<const uint32_t *>(xl4)[jj >> 1];
+                        const uint32_t bh = (jj & 1) ? (wh & 0xffff0000u) : (wh << 16), bl = (jj & 1) ? (wl & 0xffff0000u) : (wl << 16);
+                        y += __uint_as_float(bh) + __uint_as_float(bl);
                     }
+                    otile[o * OT + r] = y;
                 }
-#pragma unroll
-                for (int jj = 0; jj < 32; jj++) {
-                    const int o = cb + jj;
-                    if (o < C) {
-                        float y = v[jj] + __ldg(z.bf + o);
-                        if (z.z_residual) {
-                            const uint32_t wh = reinterpret_cast<const uint32_t *>(xh4)[jj >> 1], wl = reinterpret_cast<const uint32_t *>(xl4)[jj >> 1];
-                            const uint32_t bh = (jj & 1) ? (wh & 0xffff0000u) : (wh << 16), bl = (jj & 1) ? (wl & 0xffff0000u) : (wl << 16);
-                            y += __uint_as_float(bh) + __uint_as_float(bl);
-                        }
-                        if (z.add_ref && rb) y += __ldg(rb + (int64_t)o * z.ref_stride[1]);
-                        yb[(int64_t)o * z.y_stride[1]] = y;
-                    }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    {
+        const bool addr = z.ref && z.add_ref;
+        const bool vec = (z.y_stride[3] == 1) && (z.y_stride[2] == W) && (HW % 4 == 0) && (z.y_stride[1] % 4 == 0) && (z.y_stride[0] % 4 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(z.y) & 15) == 0) &&
+                         (!addr || ((z.ref_stride[3] == 1) && (z.ref_stride[2] == W) && (z.ref_stride[1] % 4 == 0) && (z.ref_stride[0] % 4 == 0) &&
+                                    ((reinterpret_cast<uintptr_t>(z.ref) & 15) == 0)));
+        const int pp = lane * 4, p = p0 + pp;
+        for (int o = warp; o < C; o += NT / 32) {
+            const float4 t = *reinterpret_cast<const float4 *>(otile + o * OT + pp);
+            float y[4] = {t.x, t.y, t.z, t.w};
+            if (vec && p + 3 < HW) {
+                if (addr) {
+                    const float4 r4 = __ldg(reinterpret_cast<const float4 *>(z.ref + (int64_t)n * z.ref_stride[0] + (int64_t)o * z.ref_stride[1] + p));
+                    y[0] += r4.x; y[1] += r4.y; y[2] += r4.z; y[3] += r4.w;
+                }
+                *reinterpret_cast<float4 *>(z.y + (int64_t)n * z.y_stride[0] + (int64_t)o * z.y_stride[1] + p) = make_float4(y[0], y[1], y[2], y[3]);
+            } else {
+                for (int e = 0; e < 4 && p + e < HW; e++) {
+                    const int py = (p + e) / W, px = (p + e) % W;
+                    float val = y[e];
+                    if (addr) val += __ldg(z.ref + (int64_t)n * z.ref_stride[0] + (int64_t)o * z.ref_stride[1] + (int64_t)py * z.ref_stride[2] + (int64_t)px * z.ref_stride[3]);
+                    z.y[(int64_t)n * z.y_stride[0] + (int64_t)o * z.y_stride[1] + (int64_t)py * z.y_stride[2] + (int64_t)px * z.y_stride[3]] = val;
                 }
             }
         }

@@ -35,10 +35,10 @@ class ViewParallelFusion:
     """
 
     def __init__(self, KRT_all, sampler: Optional[Callable] = None, group=None, fuse_fn: Optional[Callable] = None,
-                 exchange: str = "p2p"):
+                 exchange: str = "p2p", sync: str = "signal"):
         """exchange='peer': the per-view maps live in symmetric (peer-mapped) memory and the fused kernels read the
         source view's map straight out of the neighbour GPU's HBM over NVLink — no copy, no collective, one
-        device-side barrier per step; exchange='p2p': NCCL send/recv permutation (each rank receives only its
+        pairwise device-side signal per step (sync='barrier' restores the all-ranks barrier); exchange='p2p': NCCL send/recv permutation (each rank receives only its
         source view's map); exchange='allgather': every rank receives all maps (what BASELINE config 4 names and
         what MULTITEST-style all-neighbour fusion needs)."""
         if exchange not in ("p2p", "allgather", "peer"):
@@ -59,6 +59,8 @@ class ViewParallelFusion:
         if self.fuse_fn is None:
             raise ValueError("sampler or fuse_fn required")
         self._buf = None
+        self._P_cache = {}
+        self.sync = sync if sync in ("signal", "barrier") else "signal"     # peer mode: pairwise signals | full barrier
 
     def gather(self, feat_view: torch.Tensor) -> torch.Tensor:
         """all-gather of the per-view feature maps -> [V,B,C,H,W] (NVLink/NVSwitch under NCCL)."""
@@ -72,8 +74,7 @@ class ViewParallelFusion:
 
     # ---- exchange='peer': symmetric memory -------------------------------------------------------------------
     def alloc_view_buffers(self, shape, dtype=torch.float32, device=None, count: int = 2):
-        """`count` peer-mapped buffers for this rank's feature map (the backbone should write its output here).
-        Two buffers used alternately need only one barrier per step (see `peer_source`)."""
+        """`count` peer-mapped buffers for this rank's feature map (the backbone should write its output here)."""
         import torch.distributed._symmetric_memory as symm
         device = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
         group = self.group if self.group is not None else dist.group.WORLD
@@ -86,12 +87,19 @@ class ViewParallelFusion:
         return self._symm_bufs
 
     def peer_source(self, slot: int) -> torch.Tensor:
-        """Barrier (all ranks have finished writing buffer `slot`), then a tensor aliasing the SOURCE rank's buffer
-        `slot` in that GPU's memory.  Reads of it travel over NVLink inside whatever kernel consumes it."""
+        """Stream-ordered hand-off, then a tensor aliasing the SOURCE rank's buffer `slot` in that GPU's memory (reads of it
+        travel over NVLink inside whatever kernel consumes it).  The hand-off is pairwise, not a barrier: this rank signals
+        the ranks that read ITS map ("my buffer `slot` is written", ordered after everything already enqueued on the current
+        stream) and waits only for the signal of its own source rank — no rank waits for a camera it does not read."""
         h = self._symm_hdls[slot]
-        h.barrier(channel=0)
         if self.world == 1:
             return self._symm_bufs[slot]
+        if self.sync == "signal":
+            for r in self.consumers:
+                h.put_signal(r, channel=0)
+            h.wait_signal(self.src, channel=0)
+        else:
+            h.barrier(channel=0)
         return h.get_buffer(self.src, self._symm_shape, self._symm_dtype)
 
     def fetch_source(self, feat_view: torch.Tensor) -> torch.Tensor:
@@ -107,13 +115,32 @@ class ViewParallelFusion:
             req.wait()
         return self._recv
 
-    def __call__(self, feat_view: torch.Tensor):
+    # ---- per-camera constants on the device (built once per (device, batch); no per-step host->device copy) -------------
+    def _P_dev(self, which: int, B: int, dev):
+        key = (which, B, str(dev))
+        t = self._P_cache.get(key)
+        if t is None:
+            t = self.KRT_all[which].to(dev).unsqueeze(0).expand(B, 3, 4).contiguous()
+            self._P_cache[key] = t
+        return t
+
+    def P_ref_dev(self, B, dev):
+        return self._P_dev(self.rank, B, dev)
+
+    def P_src_dev(self, B, dev):
+        return self._P_dev(self.src, B, dev)
+
+    def __call__(self, feat_view: torch.Tensor, slot=None):
+        """One step: exchange, then fuse this rank's view against its source view.  slot: which peer-mapped buffer
+        `feat_view` is (exchange='peer'; default = round robin, with a local copy if it is not one of them)."""
         B = feat_view.shape[0]
         if self.exchange == "peer":
             if getattr(self, "_symm_bufs", None) is None or self._symm_shape != tuple(feat_view.shape):
                 self.alloc_view_buffers(feat_view.shape, feat_view.dtype, feat_view.device)
-            slot = self._symm_i % len(self._symm_bufs)
-            self._symm_i += 1
+            if slot is None:
+                slot = self._symm_i % len(self._symm_bufs)
+                self._symm_i += 1
+            slot = slot % len(self._symm_bufs)
             if feat_view.data_ptr() != self._symm_bufs[slot].data_ptr():
                 self._symm_bufs[slot].copy_(feat_view)          # backbone did not write in place: one local copy
             feat_src = self.peer_source(slot)
@@ -122,6 +149,4 @@ class ViewParallelFusion:
         else:
             feat_src = self.gather(feat_view)[self.src]
         dev = feat_view.device
-        P_ref = self.KRT_all[self.rank].to(dev).unsqueeze(0).expand(B, 3, 4).contiguous()
-        P_src = self.KRT_all[self.src].to(dev).unsqueeze(0).expand(B, 3, 4).contiguous()
-        return self.fuse_fn(feat_view, feat_src, P_ref, P_src)
+        return self.fuse_fn(feat_view, feat_src, self._P_dev(self.rank, B, dev), self._P_dev(self.src, B, dev))

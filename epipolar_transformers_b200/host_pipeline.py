@@ -4,9 +4,10 @@ The reference's test loop moves every batch host->device before the model call a
 afterwards (/root/reference/engine/tester.py:131-134, modeling/model.py:282-300).  On a B200 the fused layer
 takes ~0.3 ms while the PCIe copies of its operands take ~1 ms, so this class overlaps consecutive steps on two
 CUDA streams — host->device copies of step i+1 run while step i's kernels and device->host copies run — with
-`depth` rotating device input buffers.  (The results are copied back on the compute stream: putting them on a
-third stream makes the caching allocator wait on cross-stream events for its per-step output blocks and was
-measured slower.)  Every step's copies are still issued by that step's call; `synchronize()` drains the pipeline.
+`depth` rotating device input buffers.  With `d2h_stream=True` the results return on a THIRD stream (the step's output
+tensors are handed to it with `record_stream`), so step i+1's kernels do not queue behind step i's device->host copies;
+the default keeps them on the compute stream.  Every step's copies are still issued by that step's call;
+`synchronize()` drains the pipeline.
 """
 from __future__ import annotations
 
@@ -14,13 +15,13 @@ import torch
 
 
 class HostStreamer:
-    def __init__(self, sampler, device=None, depth: int = 2):
+    def __init__(self, sampler, device=None, depth: int = 2, d2h_stream: bool = False):
         self.sampler = sampler
         self.dev = torch.device(device if device is not None else "cuda")
         self.depth = depth
         self.s_in = torch.cuda.Stream(self.dev)
         self.s_run = torch.cuda.Stream(self.dev)
-        self.s_out = self.s_run                          # results return on the compute stream (see module docstring)
+        self.s_out = torch.cuda.Stream(self.dev) if d2h_stream else self.s_run
         self._slots = [None] * depth
         self._free = [torch.cuda.Event() for _ in range(depth)]      # slot's device inputs may be overwritten
         self._i = 0
@@ -49,9 +50,18 @@ class HostStreamer:
             self.s_run.wait_event(ev_in)
             out, corr, attn, _ = self.sampler(s["ref"], s["src"], s["P1"], s["P2"])
             self._free[k].record(self.s_run)
+            if self.s_out is self.s_run:
+                for d, t in ((h_out, out), (h_attn, attn), (h_corr, corr)):
+                    if d is not None and t is not None:
+                        d.copy_(t, non_blocking=True)
+                return
+            ev_run = torch.cuda.Event(); ev_run.record(self.s_run)
+        with torch.cuda.stream(self.s_out):
+            self.s_out.wait_event(ev_run)
             for d, t in ((h_out, out), (h_attn, attn), (h_corr, corr)):
                 if d is not None and t is not None:
+                    t.record_stream(self.s_out)          # the allocator must not recycle the block before the copy ran
                     d.copy_(t, non_blocking=True)
 
     def synchronize(self):
-        self.s_in.synchronize(); self.s_run.synchronize()
+        self.s_in.synchronize(); self.s_run.synchronize(); self.s_out.synchronize()

@@ -162,6 +162,8 @@ int epi_umma_selftest(int mode, const float *A, const float *B, float *D, int N,
  * synchronises on them and returns that launch's duration in milliseconds (< 0 if there is none). */
 int epi_kernel_timing_enable(int on);
 float epi_kernel_timing_last_ms(void);
+/* same, per launch group: ms3[0] operand staging, ms3[1] fused attention kernel, ms3[2] epilogue pass */
+int epi_kernel_timing_last3(float *ms3);
 
 /* Number of kernels the last successful epi_fusion_forward_f32 on this thread launched. */
 int epi_last_launch_count(void);

@@ -24,12 +24,12 @@ v = np.array(list(buf), dtype=np.float64)
 items = v[8]
 print("items %d (tiles %d)" % (items, N * ((H * W + 31) // 32)))
 names = {0: "W bar(top)", 1: "W wait desc", 2: "W wait S", 3: "W B1+bar", 4: "W B2a sims", 5: "W B2b softmax+scatter", 6: "W argmax+wait O(j-1)", 7: "W beta conv+bar", 9: "W epilogue",
-         10: "S wait desc_free", 11: "S build item", 13: "G issue/work", 14: "G wait f_empty", 15: "G wait desc", 16: "G wait q_empty",
+         10: "S wait desc_free", 28: "S claim+bar", 29: "S pix/ends/zero+bar", 30: "S mark+bar", 31: "S prefix+bar", 17: "S idx fill+bar", 18: "S pad+bar", 11: "S arrive/rest", 13: "G issue/work", 14: "G wait f_empty", 15: "G wait desc", 16: "G wait q_empty",
          20: "M issue/work", 21: "M wait beta", 22: "M wait o_empty", 23: "M wait f_full (G2)", 24: "M wait desc", 25: "M wait s_empty",
          26: "M wait q_full", 27: "M wait f_full (G1)"}
 for k in sorted(names):
     print("%-24s %9.0f cyc/item" % (names[k], v[k] / max(items, 1)))
-for lo, hi, nm in ((0, 8, "workers(excl epi)"), (10, 12, "setup"), (13, 17, "gather"), (20, 28, "mma")):
+for lo, hi, nm in ((0, 8, "workers(excl epi)"), (10, 12, "setup(part)"), (13, 17, "gather"), (20, 28, "mma")):
     print("%-10s total %9.0f cyc/item" % (nm, v[lo:hi].sum() / max(items, 1)))
 
 sb = (ctypes.c_ulonglong * 16)()
