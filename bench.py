@@ -87,7 +87,7 @@ def make_config(args, wl, world):
 class ClockSampler:
     """Polls SM clock / throttle reasons through NVML while the timed regions run."""
 
-    def __init__(self, index=0, period=0.005):
+    def __init__(self, index=0, period=0.02):
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = threading.Event()
         self._t = None

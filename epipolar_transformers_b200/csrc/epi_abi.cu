@@ -202,7 +202,7 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
         const bool z_planes = pl.has_z && epi::zgemm_supported(p->C);
         __nv_bfloat16 *wpl = z_planes ? reinterpret_cast<__nv_bfloat16 *>(ws + pl.off_wplanes) : nullptr;
         e = epi::launch_stage(p->feat_ref, p->ref_stride, p->feat_src, p->src_stride, planes, p->P_ref, p->P_src, pg, order, okey,
-                              z_planes ? p->z_weight_folded : nullptr, wpl, words, p->N, p->C, p->H, p->W, a.geom, st);
+                              z_planes ? p->z_weight_folded : nullptr, wpl, p->z_residual ? 1 : 0, words, p->N, p->C, p->H, p->W, a.geom, st);
         if (e != cudaSuccess) return fail(EPI_ECUDA, "operand staging launch failed: %s", cudaGetErrorString(e));
         launches++;
         w_hi = wpl; w_lo = wpl ? wpl + (size_t)p->C * p->C : nullptr;

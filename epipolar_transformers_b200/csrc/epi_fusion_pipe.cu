@@ -260,10 +260,15 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
         PT_DECL;
         int j = 0;
         for (;; j++) {
-            named_bar(1, NT_WORK);                        // everyone is done with item j-1's table and item j-2's epilogue
+            // Only warp 0 polls the mbarriers (item descriptor, then its scores); the other 15 warps sleep in the hardware
+            // barrier instead of spinning through issue slots.  The barrier also separates item j-1's use of the table.
+            if (warp == 0) {
+                wait_n(&ct.desc_full[j % NDESC], (uint32_t)(j / NDESC));
+                if (desc_at(j).tile >= 0) wait_n(&ct.s_full[j & 1], (uint32_t)(j >> 1));
+            }
+            named_bar(1, NT_WORK);
             PT(0);
             if (tid == 0 && j >= 2) mbar_arrive(&ct.desc_free[(j - 2) % NDESC]);
-            wait_n(&ct.desc_full[j % NDESC], (uint32_t)(j / NDESC));
             const Desc &d = desc_at(j);
             PT(1);
             if (d.tile < 0) break;
@@ -271,7 +276,6 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
             const int nch = (D + CHUNK - 1) / CHUNK;
 
             // ---------------- B1: scores TMEM -> T[rank][pixel] ----------------
-            wait_n(&ct.s_full[j & 1], (uint32_t)(j >> 1));
             tc_fence_after();
             PT(2);
             {
@@ -389,6 +393,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 }
             }
             if (a.corr_pos) { red_bv[warp * 32 + lane] = best_v; red_bk[warp * 32 + lane] = best_k; }
+            if (warp == 0 && j >= 1) wait_n(&ct.o_full[(j - 1) & 1], (uint32_t)((j - 1) >> 1));   // GEMM2(j-1) has consumed the β panels
             named_bar(1, NT_WORK);
             PT(5);
             // ---------------- arg-max -> corr_pos (first maximum, like torch.argmax) ----------------
@@ -410,7 +415,6 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 reinterpret_cast<float2 *>(a.corr_pos)[(size_t)n * HW + pofs] = make_float2(grid2corr(gx, W, gc.correct), grid2corr(gy, H, gc.correct));
             }
             // ---------------- β[rank][pixel] -> bf16 (hi, lo) stacked K-major panels; warp <-> 16 ranks, lane <-> pixel ----------------
-            if (j >= 1) wait_n(&ct.o_full[(j - 1) & 1], (uint32_t)((j - 1) >> 1));   // GEMM2(j-1) has consumed the β panels
             PT(6);
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
@@ -437,7 +441,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
 #endif
         }
         if (j >= 1) {                                   // drain
-            wait_n(&ct.o_full[(j - 1) & 1], (uint32_t)((j - 1) >> 1));
+            if (warp == 0) wait_n(&ct.o_full[(j - 1) & 1], (uint32_t)((j - 1) >> 1));
+            named_bar(1, NT_WORK);
             tc_fence_after();
             epilogue(j - 1);
         }
@@ -472,7 +477,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
         };
         for (int j = 0;; j++) {
             Desc &d = desc_at(j);
-            if (j >= NDESC) wait_n(&ct.desc_free[j % NDESC], (uint32_t)(j / NDESC - 1));
+            if (st == 0 && j >= NDESC) wait_n(&ct.desc_free[j % NDESC], (uint32_t)(j / NDESC - 1));   // the claim barrier below releases the rest
             PT(10);
             bool done = false;
             while (true) {
@@ -609,7 +614,10 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
         auto stage_acquire = [&]() -> uint8_t * {
             const uint32_t s = fcount % NSTAGE;
             PT(13);
-            if (fcount >= NSTAGE) wait_n(&ct.f_empty[s], fcount / NSTAGE - 1);
+            if (fcount >= NSTAGE) {
+                if (gt < 32) wait_n(&ct.f_empty[s], fcount / NSTAGE - 1);
+                named_bar(3, NGATHER);
+            }
             PT(14);
             return smem + OFF_STAGE + s * STAGE_BYTES;
         };
@@ -646,13 +654,17 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
         };
         for (int j = 0;; j++) {
             PT(13);
-            wait_n(&ct.desc_full[j % NDESC], (uint32_t)(j / NDESC));
+            if (gt < 32) wait_n(&ct.desc_full[j % NDESC], (uint32_t)(j / NDESC));
+            named_bar(3, NGATHER);
             PT(15);
             const Desc &d = desc_at(j);
             const bool last = d.tile < 0;
             if (!last && d.D > 0) {
                 // ---- query rows of the item's pixels: stacked panels [hi 32 rows | lo 32 rows] x NP ----
-                if (qcount >= 1) wait_n(&ct.q_empty, qcount - 1);
+                if (qcount >= 1) {
+                    if (gt < 32) wait_n(&ct.q_empty, qcount - 1);
+                    named_bar(3, NGATHER);
+                }
                 PT(16);
                 {
                     const __nv_bfloat16 *ref = planes + (size_t)d.n * HW * C;

@@ -57,7 +57,7 @@ struct ZArgs {
 // tensor-core z-projection: x arrives as bf16 (hi, lo) planes [N,H,W,C] written by the tile kernel
 struct ZGemmArgs {
     const __nv_bfloat16 *x_hi, *x_lo;
-    const __nv_bfloat16 *w_hi, *w_lo;         // Wf [C out][C in] as bf16 (hi, lo) planes (written by the staging kernel)
+    const __nv_bfloat16 *w_hi, *w_lo;         // Wf (+ I when ZRESIDUAL) [C out][C in] as bf16 (hi, lo) planes (written by the staging kernel)
     const float *Wf, *bf;
     const float *ref;       int64_t ref_stride[4];
     float *y;               int64_t y_stride[4];
@@ -79,8 +79,8 @@ cudaError_t launch_split_planes(const float *src, const int64_t stride[4], __nv_
 
 cudaError_t launch_stage(const float *ref, const int64_t ref_stride[4], const float *src, const int64_t src_stride[4],
                          __nv_bfloat16 *planes, const float *P_ref, const float *P_src, PairGeom *pair_geom, uint16_t *order,
-                         float *order_key, const float *Wf, __nv_bfloat16 *w_planes, int *zero_words, int N, int C, int H, int W,
-                         const GeomCfg &gc, cudaStream_t st);
+                         float *order_key, const float *Wf, __nv_bfloat16 *w_planes, int w_add_identity, int *zero_words, int N, int C,
+                         int H, int W, const GeomCfg &gc, cudaStream_t st);
 
 cudaError_t launch_nchw_to_nhwc(const float *src, const int64_t stride[4], float *dst, int N, int C, int H, int W, cudaStream_t st);
 cudaError_t launch_z_epilogue(const ZArgs &z, cudaStream_t st);

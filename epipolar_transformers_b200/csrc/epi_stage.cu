@@ -19,6 +19,8 @@ namespace stg {
 constexpr int NT = 256;
 constexpr int NBIN = 4096;
 constexpr int SMALL = 32;
+constexpr int TC = 64, TPX = 128, TPITCH = 129;     // layout-staging tile: 64 channels x 128 pixels (512-byte DRAM bursts per channel row,
+                                                    // 128-byte plane segments per pixel)
 
 // Monotone pseudo-angle of (u, v) in [-2, 2] (diamond angle): same ordering as atan2(v, u) at the price of one division.
 __device__ __forceinline__ float pseudo_angle(float u, float v) {
@@ -59,6 +61,7 @@ struct StageArgs {
     int *zero_words;                  // tile counter, error word
     float *order_key;                 // optional [N][32]: key of the cached (order, pair constants); null = rebuild every call
     const float *Wf;                  // optional [C][C] folded z weight -> bf16 (hi, lo) planes w_planes [2][C][C]
+    int w_add_identity;               // ZRESIDUAL folded into the weight: planes hold Wf + I
     __nv_bfloat16 *w_planes;
     int N, C, H, W;
     int do_ref, do_src, do_order;
@@ -68,8 +71,8 @@ struct StageArgs {
 // (min 5 blocks per SM: the layout-staging blocks need few registers; the rare order blocks may spill a little)
 __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s) {
     using namespace stg;
-    extern __shared__ __align__(16) uint8_t dyn[];        // transposition tile [64][65] fp32 | order blocks: histogram + pixel list
-    float (*tile)[65] = reinterpret_cast<float (*)[65]>(dyn);
+    extern __shared__ __align__(16) uint8_t dyn[];        // transposition tile [64 ch][129] fp32 | order blocks: histogram + pixel list
+    float (*tile)[TPITCH] = reinterpret_cast<float (*)[TPITCH]>(dyn);
     const int t = threadIdx.x;
     const int H = s.H, W = s.W, HW = H * W, C = s.C;
     const int nord = s.do_order ? s.N : 0;
@@ -243,7 +246,7 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
     // ----------------------------------------------------------------------------------------------------
     // layout staging: 64 channels x 64 pixels per block
     // ----------------------------------------------------------------------------------------------------
-    const int tiles_p = (HW + 63) / 64, tiles_c = (C + 63) / 64;
+    const int tiles_p = (HW + TPX - 1) / TPX, tiles_c = (C + TC - 1) / TC;
     const int per_map = tiles_p * tiles_c * s.N;
     int lin = (int)blockIdx.x - nord;
     if (lin >= 2 * per_map) {
@@ -251,7 +254,11 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
         const size_t e0 = ((size_t)(lin - 2 * per_map) * NT + t) * 8, tot = (size_t)C * C;
         if (e0 < tot) {
             const float4 a4 = __ldg(reinterpret_cast<const float4 *>(s.Wf + e0)), b4 = __ldg(reinterpret_cast<const float4 *>(s.Wf + e0 + 4));
-            const float f[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+            float f[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
+            if (s.w_add_identity) {                           // y = Wf·x + x  ==  (Wf + I)·x : the ZRESIDUAL costs nothing in the GEMM
+                const int o = (int)(e0 / C), c_first = (int)(e0 % C);
+                if (o >= c_first && o < c_first + 8) f[o - c_first] += 1.f;
+            }
             uint32_t h[4], l[4];
 #pragma unroll
             for (int u = 0; u < 4; u++) {
@@ -270,7 +277,7 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
     if (s.do_ref && s.do_src) { map = lin >= per_map; lin -= map * per_map; }
     else map = s.do_src ? 1 : 0;
     const int n = lin / (tiles_p * tiles_c), rem = lin % (tiles_p * tiles_c);
-    const int c0 = (rem / tiles_p) * 64, p0 = (rem % tiles_p) * 64;
+    const int c0 = (rem / tiles_p) * TC, p0 = (rem % tiles_p) * TPX;
     const float *base = map ? s.src : s.ref;
     const int64_t *strd = map ? s.src_stride : s.ref_stride;
     const int64_t sn = strd[0], sc = strd[1], sh = strd[2], sw = strd[3];
@@ -279,11 +286,11 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
     __nv_bfloat16 *hi = s.planes + (size_t)(2 * map) * plane_elems, *lo = hi + plane_elems;
     const bool vec = (sw == 1) && (sh == W) && (HW % 4 == 0) && (sc % 4 == 0) && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0);
     if (sc != 1) {
-        const int q = t & 15, cy = t >> 4;                      // 16 float4 per channel row, 16 channels per pass
-        float4 v[4];
+        const int q = t & 31, cy = t >> 5;                      // 32 float4 per channel row (one 512-byte burst per warp), 8 channels per pass
+        float4 v[8];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int c = c0 + cy + i * 16, p = p0 + q * 4;
+        for (int i = 0; i < 8; i++) {
+            const int c = c0 + cy + i * 8, p = p0 + q * 4;
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c < C) {
                 if (vec && p + 3 < HW) v[i] = __ldg(reinterpret_cast<const float4 *>(sp + c * sc + p));
@@ -295,22 +302,22 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            float *row = &tile[cy + i * 16][q * 4];
+        for (int i = 0; i < 8; i++) {
+            float *row = &tile[cy + i * 8][q * 4];
             row[0] = v[i].x; row[1] = v[i].y; row[2] = v[i].z; row[3] = v[i].w;
         }
     } else {
-        const int cx = t & 63, py = t >> 6;                     // channels-last: a warp reads 32 consecutive channels
+        const int cx = t & 63, py = t >> 6;                     // channels-last: a warp reads 32 consecutive channels of one pixel
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
+        for (int i = 0; i < 32; i++) {
             const int p = p0 + py + i * 4, c = c0 + cx;
             tile[cx][py + i * 4] = (c < C && p < HW) ? __ldg(sp + c + (p / W) * sh + (p % W) * sw) : 0.f;
         }
     }
     __syncthreads();
-    const int cg = t & 7, pl = t >> 3;                          // 8 channel groups x 32 pixels per pass
+    const int cg = t & 7, pl = t >> 3;                          // 8 groups of 8 channels (128 contiguous bytes per pixel and plane) x 32 pixels per pass
 #pragma unroll
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < 4; i++) {
         const int pp = pl + i * 32, p = p0 + pp, c = c0 + cg * 8;
         if (p < HW && c < C) {                                  // C % 8 == 0 on this path
             uint32_t h[4], l[4];
@@ -332,19 +339,19 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
 
 cudaError_t launch_stage(const float *ref, const int64_t ref_stride[4], const float *src, const int64_t src_stride[4],
                          __nv_bfloat16 *planes, const float *P_ref, const float *P_src, PairGeom *pair_geom, uint16_t *order,
-                         float *order_key, const float *Wf, __nv_bfloat16 *w_planes, int *zero_words, int N, int C, int H, int W,
-                         const GeomCfg &gc, cudaStream_t st) {
+                         float *order_key, const float *Wf, __nv_bfloat16 *w_planes, int w_add_identity, int *zero_words, int N, int C,
+                         int H, int W, const GeomCfg &gc, cudaStream_t st) {
     StageArgs s;
     s.ref = ref; s.src = src;
     for (int i = 0; i < 4; i++) { s.ref_stride[i] = ref_stride[i]; s.src_stride[i] = src_stride[i]; }
-    s.planes = planes; s.P_ref = P_ref; s.P_src = P_src; s.pair_geom = pair_geom; s.order = order; s.order_key = order_key; s.Wf = Wf; s.w_planes = w_planes;
+    s.planes = planes; s.P_ref = P_ref; s.P_src = P_src; s.pair_geom = pair_geom; s.order = order; s.order_key = order_key; s.Wf = Wf; s.w_planes = w_planes; s.w_add_identity = w_add_identity;
     s.zero_words = zero_words; s.N = N; s.C = C; s.H = H; s.W = W; s.gc = gc;
     s.do_ref = 1; s.do_src = 1; s.do_order = (P_ref && P_src && order) ? 1 : 0;
-    const int tiles = ((H * W + 63) / 64) * ((C + 63) / 64) * N;
+    const int tiles = ((H * W + stg::TPX - 1) / stg::TPX) * ((C + stg::TC - 1) / stg::TC) * N;
     const int wblocks = (Wf && w_planes) ? (C * C / 8 + stg::NT - 1) / stg::NT : 0;        // C % 8 == 0
     const int grid = (s.do_order ? N : 0) + 2 * tiles + wblocks;
     // dynamic shared memory: the transposition tile, or (order blocks) 16 KB histogram + 2 B per pixel
-    size_t smem = 64 * 65 * sizeof(float);
+    size_t smem = (size_t)stg::TC * stg::TPITCH * sizeof(float);
     if (s.do_order && (size_t)stg::NBIN * 4 + (size_t)H * W * 2 > smem) smem = (size_t)stg::NBIN * 4 + (size_t)H * W * 2;
     static thread_local size_t smem_set = 0;
     if (smem + 1024 > 48 * 1024 && smem > smem_set) {        // (+ the kernel's small static arrays)

@@ -105,43 +105,21 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
     tc_fence_after();
 
     // ---- epilogue ------------------------------------------------------------------------------------------------
-    // phase 1 (thread <-> pixel = TMEM lane, 16 warps = 4 lane quadrants x 4 channel groups): accumulator + bias (+ ZRESIDUAL, read
-    //   from the pixel-major bf16 planes as 16-byte chunks) -> shared tile [channel][128 pixels] (the operand stages are free now);
-    // phase 2 (warp <-> channel row, lane <-> 4 consecutive pixels): + caller residual, 512-byte row segments of the NCHW output
+    // phase 1 (thread <-> pixel = TMEM lane, 16 warps = 4 lane quadrants x 4 channel groups): accumulator -> shared tile
+    //   [channel][128 pixels] (the operand stages are free now).  The ZRESIDUAL needs no pass: the staged weight is Wf + I;
+    // phase 2 (warp <-> channel row, lane <-> 4 consecutive pixels): + bias + caller residual, 512-byte row segments of the NCHW output
     //   per warp instruction.  Falls back to per-element addressing for strides that are not pixel-contiguous.
     float *otile = reinterpret_cast<float *>(smem);            // [C][132] fp32 <= 256 * 132 * 4 = 135168 B of the 196608 B stage area
     constexpr int OT = 132;
     {
-        const int r = (warp & 3) * 32 + lane, p = p0 + r;
-        const bool ok = p < HW;
+        const int r = (warp & 3) * 32 + lane;
         for (int cb = (warp >> 2) * 32; cb < C; cb += 128) {
             float v[32];
             tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + cb, v);
-            uint4 xh4[4], xl4[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) { xh4[u] = make_uint4(0, 0, 0, 0); xl4[u] = make_uint4(0, 0, 0, 0); }
-            if (ok && z.z_residual) {
-#pragma unroll
-                for (int u = 0; u < 4; u++)
-                    if (cb + u * 8 < C) {
-                        xh4[u] = __ldg(reinterpret_cast<const uint4 *>(xh + (size_t)p * C + cb + u * 8));
-                        xl4[u] = __ldg(reinterpret_cast<const uint4 *>(xl + (size_t)p * C + cb + u * 8));
-                    }
-            }
             tmem_ld_wait();
 #pragma unroll
-            for (int jj = 0; jj < 32; jj++) {
-                const int o = cb + jj;
-                if (o < C) {
-                    float y = v[jj] + __ldg(z.bf + o);
-                    if (z.z_residual) {
-                        const uint32_t wh = reinterpret_cast<const uint32_t *>(xh4)[jj >> 1], wl = reinterpret_cast<const uint32_t *>(xl4)[jj >> 1];
-                        const uint32_t bh = (jj & 1) ? (wh & 0xffff0000u) : (wh << 16), bl = (jj & 1) ? (wl & 0xffff0000u) : (wl << 16);
-                        y += __uint_as_float(bh) + __uint_as_float(bl);
-                    }
-                    otile[o * OT + r] = y;
-                }
-            }
+            for (int jj = 0; jj < 32; jj++)
+                if (cb + jj < C) otile[(cb + jj) * OT + r] = v[jj];
         }
     }
     tc_fence_before();
@@ -155,7 +133,8 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
         const int pp = lane * 4, p = p0 + pp;
         for (int o = warp; o < C; o += NT / 32) {
             const float4 t = *reinterpret_cast<const float4 *>(otile + o * OT + pp);
-            float y[4] = {t.x, t.y, t.z, t.w};
+            const float b = __ldg(z.bf + o);
+            float y[4] = {t.x + b, t.y + b, t.z + b, t.w + b};
             if (vec && p + 3 < HW) {
                 if (addr) {
                     const float4 r4 = __ldg(reinterpret_cast<const float4 *>(z.ref + (int64_t)n * z.ref_stride[0] + (int64_t)o * z.ref_stride[1] + p));
