@@ -458,22 +458,21 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
         float tk[KPL];                                      // this lane's sample parameters k/(K-1), k = lane + 32 jj
 #pragma unroll
         for (int jj = 0; jj < KPL; jj++) tk[jj] = (float)(lane + 32 * jj) / (float)(K - 1);
-        // every in-bounds pixel of the 2x2 bilinear footprint (a superset of the taps with non-zero weight)
+        // every in-bounds pixel of the 2x2 bilinear footprint (a superset of the taps with non-zero weight): one atomicOr per
+        // footprint row (two only when the row's pixels straddle a 32-bit word)
         auto mark = [&](Desc &d, float gx, float gy) {
             const float ix = grid2pix(gx, W, gc.align), iy = grid2pix(gy, H, gc.align);
             if (!(ix > -1.f && ix < (float)W && iy > -1.f && iy < (float)H)) return;       // also rejects NaN / far sentinels
             const int x0 = (int)floorf(ix), y0 = (int)floorf(iy);                          // -1 .. size-1
-            const bool xin0 = x0 >= 0, xin1 = x0 + 1 < W, yin0 = y0 >= 0, yin1 = y0 + 1 < H;
-            const int p00 = y0 * W + x0;
-            if (yin0) {
-                if (xin0) atomicOr(&d.bitmap[p00 >> 5], 1u << (p00 & 31));
-                if (xin1) atomicOr(&d.bitmap[(p00 + 1) >> 5], 1u << ((p00 + 1) & 31));
-            }
-            if (yin1) {
-                const int p10 = p00 + W;
-                if (xin0) atomicOr(&d.bitmap[p10 >> 5], 1u << (p10 & 31));
-                if (xin1) atomicOr(&d.bitmap[(p10 + 1) >> 5], 1u << ((p10 + 1) & 31));
-            }
+            const uint32_t mbits = x0 < 0 ? 1u : (x0 + 1 < W ? 3u : 1u);                   // pixels max(x0,0) [, x0+1]
+            const int pos = y0 * W + max(x0, 0);
+            auto row = [&](int ps) {
+                const uint32_t sh = (uint32_t)ps & 31u;
+                atomicOr(&d.bitmap[ps >> 5], mbits << sh);
+                if (sh == 31u && mbits == 3u) atomicOr(&d.bitmap[(ps >> 5) + 1], 1u);
+            };
+            if (y0 >= 0) row(pos);
+            if (y0 + 1 < H) row(pos + W);
         };
         for (int j = 0;; j++) {
             Desc &d = desc_at(j);
@@ -624,26 +623,34 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
         auto arrive_async = [&](uint64_t *bar) {
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
         };
+        // shared-memory offset of this thread's 16-byte chunk inside a 128-byte-row panel: rows gr + 16·it keep (row & 7) = gr & 7
+        const uint32_t so0 = (uint32_t)gr * 128u + (uint32_t)((gj ^ (gr & 7)) << 4);
+        const uint32_t smem_base = smem_u32(smem);
+        auto cp16 = [&](uint32_t dst, const __nv_bfloat16 *srcp, bool valid) {
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(srcp), "r"(valid ? 16 : 0) : "memory");
+        };
         auto gemm2_stages = [&](int jj) {
             const Desc &d = desc_at(jj);
             const int D16 = (d.D + 15) & ~15, nblk = (D16 + 63) >> 6;
             const __nv_bfloat16 *src = planes + 2 * plane_elems + (size_t)d.n * HW * C;
-            for (int h = 0; h < NH; h++)
-                for (int blk = 0; blk < nblk; blk++) {
-                    uint8_t *stg = stage_acquire();
-                    const int rows = min(64, D16 - blk * 64);
+            for (int blk = 0; blk < nblk; blk++) {               // (block of 64 union rows) outer, channel half inner: row addresses are
+                const int rows = min(64, D16 - blk * 64);        // computed once per block
+                uint32_t roff[4];
+#pragma unroll
+                for (int it = 0; it < 4; it++) roff[it] = (gr + 16 * it < rows) ? (uint32_t)d.idx[blk * 64 + gr + 16 * it] * (uint32_t)C : 0u;
+                for (int h = 0; h < NH; h++) {
+                    const uint32_t stg = smem_base + (uint32_t)(stage_acquire() - smem);
 #pragma unroll
                     for (int it = 0; it < 4; it++) {
-                        const int r = gr + 16 * it;
-                        if (r < rows) {
-                            const __nv_bfloat16 *row = src + (size_t)d.idx[blk * 64 + r] * C;
-                            const uint32_t so = (uint32_t)r * 128u + (uint32_t)((gj ^ (r & 7)) << 4);
+                        if (gr + 16 * it < rows) {
+                            const __nv_bfloat16 *row = src + roff[it];
+                            const uint32_t so = so0 + (uint32_t)it * 2048u;
 #pragma unroll
                             for (int pn = 0; pn < 2; pn++) {
                                 const int ch = (h * 2 + pn) * 64 + gj * 8;
                                 if (ch < C) {
-                                    cp_async16(stg + pn * 8192 + so, row + ch, true);
-                                    cp_async16(stg + PLANE_BYTES + pn * 8192 + so, row + plane_elems + ch, true);
+                                    cp16(stg + pn * 8192 + so, row + ch, true);
+                                    cp16(stg + PLANE_BYTES + pn * 8192 + so, row + plane_elems + ch, true);
                                 }
                             }
                         }
@@ -651,6 +658,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     arrive_async(&ct.f_full[fcount % NSTAGE]);
                     fcount++;
                 }
+            }
         };
         for (int j = 0;; j++) {
             PT(13);
@@ -673,37 +681,40 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                         const int r = gr + 16 * it;
                         const uint32_t p = d.pix[r];
                         const __nv_bfloat16 *row = ref + (size_t)(p == 0xFFFFFFFFu ? 0 : (int)(p >> 16) * W + (int)(p & 0xffffu)) * C;
-                        const uint32_t so = (uint32_t)r * 128u + (uint32_t)((gj ^ (r & 7)) << 4);
+                        const uint32_t so = smem_base + OFF_Q + so0 + (uint32_t)it * 2048u;
 #pragma unroll
                         for (int kp = 0; kp < 4; kp++) {
                             const int ch = kp * 64 + gj * 8;
                             if (kp < NP) {                  // channels beyond C are zero-filled: they are part of the MMA K range
                                 const bool ok = ch < C;
-                                cp_async16(smem + OFF_Q + kp * PANEL_B2 + so, ok ? row + ch : row, ok);
-                                cp_async16(smem + OFF_Q + kp * PANEL_B2 + 4096 + so, ok ? row + plane_elems + ch : row, ok);
+                                cp16(so + kp * PANEL_B2, ok ? row + ch : row, ok);
+                                cp16(so + kp * PANEL_B2 + 4096, ok ? row + plane_elems + ch : row, ok);
                             }
                         }
                     }
                 }
                 arrive_async(&ct.q_full);
                 qcount++;
-                // ---- GEMM1 stages: (chunk, 64-channel panel) ----
+                // ---- GEMM1 stages: (chunk, 64-channel panel); the row addresses of a chunk are computed once for its NP panels ----
                 const int D16 = (d.D + 15) & ~15, nch = (d.D + CHUNK - 1) / CHUNK;
                 const __nv_bfloat16 *src = planes + 2 * plane_elems + (size_t)d.n * HW * C;
                 for (int c = 0; c < nch; c++) {
                     const int rows = min(CHUNK, D16 - c * CHUNK);
+                    uint32_t roff[8];
+#pragma unroll
+                    for (int it = 0; it < 8; it++) roff[it] = (gr + 16 * it < rows) ? (uint32_t)d.idx[c * CHUNK + gr + 16 * it] * (uint32_t)C : 0u;
                     for (int kp = 0; kp < NP; kp++) {
-                        uint8_t *stg = stage_acquire();
+                        const uint32_t stg = smem_base + (uint32_t)(stage_acquire() - smem);
                         const int ch = kp * 64 + gj * 8;
+                        const bool ok = ch < C;
+                        const __nv_bfloat16 *colp = src + (ok ? ch : 0);
 #pragma unroll
                         for (int it = 0; it < 8; it++) {
-                            const int r = gr + 16 * it;
-                            if (r < rows) {
-                                const bool ok = ch < C;
-                                const __nv_bfloat16 *row = src + (size_t)d.idx[c * CHUNK + r] * C + (ok ? ch : 0);
-                                const uint32_t so = (uint32_t)r * 128u + (uint32_t)((gj ^ (r & 7)) << 4);
-                                cp_async16(stg + so, row, ok);
-                                cp_async16(stg + PLANE_BYTES + so, row + plane_elems, ok);
+                            if (gr + 16 * it < rows) {
+                                const __nv_bfloat16 *row = colp + roff[it];
+                                const uint32_t so = stg + so0 + (uint32_t)it * 2048u;
+                                cp16(so, row, ok);
+                                cp16(so + PLANE_BYTES, row + plane_elems, ok);
                             }
                         }
                         arrive_async(&ct.f_full[fcount % NSTAGE]);
@@ -737,8 +748,8 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
             if (d.D > 0) {
                 const int D16 = (d.D + 15) & ~15, nblk = (D16 + 63) >> 6;
                 const uint32_t idesc64 = make_idesc_bf16(128, 2 * P, 1, 0), idesc32 = make_idesc_bf16(128, P, 1, 0);
-                for (int h = 0; h < NH; h++)
-                    for (int blk = 0; blk < nblk; blk++) {
+                for (int blk = 0; blk < nblk; blk++)
+                    for (int h = 0; h < NH; h++) {
                         const uint32_t s = fcount % NSTAGE;
                         PT(20);
                         wait_n(&ct.f_full[s], fcount / NSTAGE);

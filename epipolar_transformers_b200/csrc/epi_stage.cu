@@ -19,8 +19,8 @@ namespace stg {
 constexpr int NT = 256;
 constexpr int NBIN = 4096;
 constexpr int SMALL = 32;
-constexpr int TC = 64, TPX = 128, TPITCH = 129;     // layout-staging tile: 64 channels x 128 pixels (512-byte DRAM bursts per channel row,
-                                                    // 128-byte plane segments per pixel)
+constexpr int TC = 64, TPX = 64, TPITCH = 65;       // layout-staging tile: 64 channels x 64 pixels (measured best: 16.4 us at cfg2 vs 19.4 us
+                                                    // for 64 x 128 and 22.4 us for 32 x 128 — profiles/stage_tile_sweep_r2.md)
 
 // Monotone pseudo-angle of (u, v) in [-2, 2] (diamond angle): same ordering as atan2(v, u) at the price of one division.
 __device__ __forceinline__ float pseudo_angle(float u, float v) {
@@ -71,7 +71,7 @@ struct StageArgs {
 // (min 5 blocks per SM: the layout-staging blocks need few registers; the rare order blocks may spill a little)
 __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s) {
     using namespace stg;
-    extern __shared__ __align__(16) uint8_t dyn[];        // transposition tile [64 ch][129] fp32 | order blocks: histogram + pixel list
+    extern __shared__ __align__(16) uint8_t dyn[];        // transposition tile [64 ch][65] fp32 | order blocks: histogram + pixel list
     float (*tile)[TPITCH] = reinterpret_cast<float (*)[TPITCH]>(dyn);
     const int t = threadIdx.x;
     const int H = s.H, W = s.W, HW = H * W, C = s.C;
@@ -285,12 +285,13 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
     const size_t plane_elems = (size_t)s.N * HW * C;
     __nv_bfloat16 *hi = s.planes + (size_t)(2 * map) * plane_elems, *lo = hi + plane_elems;
     const bool vec = (sw == 1) && (sh == W) && (HW % 4 == 0) && (sc % 4 == 0) && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0);
+    constexpr int QW = TPX / 4, RPP = NT / QW, RPASS = TC / RPP;        // float4 per channel row, channel rows per pass, passes
     if (sc != 1) {
-        const int q = t & 31, cy = t >> 5;                      // 32 float4 per channel row (one 512-byte burst per warp), 8 channels per pass
-        float4 v[8];
+        const int q = t % QW, cy = t / QW;
+        float4 v[RPASS];
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int c = c0 + cy + i * 8, p = p0 + q * 4;
+        for (int i = 0; i < RPASS; i++) {
+            const int c = c0 + cy + i * RPP, p = p0 + q * 4;
             v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (c < C) {
                 if (vec && p + 3 < HW) v[i] = __ldg(reinterpret_cast<const float4 *>(sp + c * sc + p));
@@ -302,23 +303,25 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
             }
         }
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-            float *row = &tile[cy + i * 8][q * 4];
+        for (int i = 0; i < RPASS; i++) {
+            float *row = &tile[cy + i * RPP][q * 4];
             row[0] = v[i].x; row[1] = v[i].y; row[2] = v[i].z; row[3] = v[i].w;
         }
     } else {
-        const int cx = t & 63, py = t >> 6;                     // channels-last: a warp reads 32 consecutive channels of one pixel
+        const int cx = t % TC, py = t / TC;                     // channels-last: a warp reads 32 consecutive channels of one pixel
+        constexpr int PPP = NT / TC;
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-            const int p = p0 + py + i * 4, c = c0 + cx;
-            tile[cx][py + i * 4] = (c < C && p < HW) ? __ldg(sp + c + (p / W) * sh + (p % W) * sw) : 0.f;
+        for (int i = 0; i < TPX / PPP; i++) {
+            const int p = p0 + py + i * PPP, c = c0 + cx;
+            tile[cx][py + i * PPP] = (c < C && p < HW) ? __ldg(sp + c + (p / W) * sh + (p % W) * sw) : 0.f;
         }
     }
     __syncthreads();
-    const int cg = t & 7, pl = t >> 3;                          // 8 groups of 8 channels (128 contiguous bytes per pixel and plane) x 32 pixels per pass
+    constexpr int CG = TC / 8, PXP = NT / CG;                    // groups of 8 channels (16 bytes per plane), pixels per pass
+    const int cg = t % CG, pl = t / CG;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const int pp = pl + i * 32, p = p0 + pp, c = c0 + cg * 8;
+    for (int i = 0; i < TPX / PXP; i++) {
+        const int pp = pl + i * PXP, p = p0 + pp, c = c0 + cg * 8;
         if (p < HW && c < C) {                                  // C % 8 == 0 on this path
             uint32_t h[4], l[4];
 #pragma unroll
