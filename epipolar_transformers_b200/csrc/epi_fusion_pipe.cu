@@ -310,48 +310,76 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
             float x[KW], tw[KW][4];
             uint32_t rk[KW][2];
             float mloc = -INFINITY;
+            // Branch-free stages over the warp's KW samples so that their dependency chains (location -> footprint -> two bitmap
+            // rank lookups -> four table reads) interleave instead of running one sample after the other.
+            {
+                float gxs[KW], gys[KW];
+                bool live[KW], firstx0[KW];
+                // stage 1: locations, footprints, weights (zero for every tap that is out of bounds or not sampled)
 #pragma unroll
-            for (int jj = 0; jj < KW; jj++) {
-                const int k = warp + NWORK * jj;
-                x[jj] = -INFINITY; rk[jj][0] = rk[jj][1] = 0u;
-#pragma unroll
-                for (int tp = 0; tp < 4; tp++) tw[jj][tp] = 0.f;
-                if (act && k < K) {
-                    float gx, gy;
+                for (int jj = 0; jj < KW; jj++) {
+                    const int k = warp + NWORK * jj;
+                    live[jj] = act && k < K;
+                    float gx = 0.f, gy = 0.f;
                     if (a.locs_in) {
-                        const float2 l = __ldg(reinterpret_cast<const float2 *>(a.locs_in) + ((size_t)k * a.N + n) * HW + pofs);
-                        gx = l.x; gy = l.y;
+                        if (live[jj]) {
+                            const float2 l = __ldg(reinterpret_cast<const float2 *>(a.locs_in) + ((size_t)k * a.N + n) * HW + pofs);
+                            gx = l.x; gy = l.y;
+                        }
                     } else {
                         gx = img2grid_x(lerp_exact(en.x, en.z, tkw[jj]), gc);
                         gy = img2grid_y(lerp_exact(en.y, en.w, tkw[jj]), gc);
                     }
-                    if (a.locs_out) reinterpret_cast<float2 *>(a.locs_out)[((size_t)k * a.N + n) * HW + pofs] = make_float2(gx, gy);
-                    float sim = 0.f;
+                    gxs[jj] = gx; gys[jj] = gy;
                     const float ix = grid2pix(gx, W, gc.align), iy = grid2pix(gy, H, gc.align);
-                    if (D > 0 && ix > -1.f && ix < (float)W && iy > -1.f && iy < (float)H) {       // else: no tap in bounds (or NaN)
-                        const float fx = floorf(ix), fy = floorf(iy);
-                        const int x0 = (int)fx, y0 = (int)fy;
-                        const float ax = ix - fx, ay = iy - fy;
-                        const bool xin0 = x0 >= 0, xin1 = x0 + 1 < W, yin0 = y0 >= 0, yin1 = y0 + 1 < H;
-                        const float w00 = (xin0 && yin0) ? (1.f - ax) * (1.f - ay) : 0.f, w01 = (xin1 && yin0) ? ax * (1.f - ay) : 0.f;
-                        const float w10 = (xin0 && yin1) ? (1.f - ax) * ay : 0.f, w11 = (xin1 && yin1) ? ax * ay : 0.f;
-                        // ranks: one bitmap lookup per footprint row (the row's second pixel is marked too, so it is rank + 1)
-                        auto rank_of = [&](int pix) { return (int)d.prefix[pix >> 5] + __popc(d.bitmap[pix >> 5] & ((1u << (pix & 31)) - 1u)); };
-                        const int p00 = y0 * W + x0;
-                        int r00 = 0, r01 = 0, r10 = 0, r11 = 0;
-                        if (yin0) { if (xin0) { r00 = rank_of(p00); r01 = r00 + 1; } else r01 = rank_of(p00 + 1); }
-                        if (yin1) { if (xin0) { r10 = rank_of(p00 + W); r11 = r10 + 1; } else r11 = rank_of(p00 + W + 1); }
-                        const int rmax = D - 1;                      // defensive: a rank can never leave the table
-                        r00 = min(r00, rmax); r01 = min(r01, rmax); r10 = min(r10, rmax); r11 = min(r11, rmax);
-                        sim = w00 * table[tix(r00, i)];
-                        sim = fmaf(w01, table[tix(r01, i)], sim);
-                        sim = fmaf(w10, table[tix(r10, i)], sim);
-                        sim = fmaf(w11, table[tix(r11, i)], sim);
-                        tw[jj][0] = w00; tw[jj][1] = w01; tw[jj][2] = w10; tw[jj][3] = w11;
-                        rk[jj][0] = (uint32_t)r00 | ((uint32_t)r01 << 16); rk[jj][1] = (uint32_t)r10 | ((uint32_t)r11 << 16);
+                    const bool in = live[jj] && ix > -1.f && ix < (float)W && iy > -1.f && iy < (float)H;   // else no tap in bounds (or NaN)
+                    const float fx = in ? floorf(ix) : 0.f, fy = in ? floorf(iy) : 0.f;
+                    const int x0 = (int)fx, y0 = (int)fy;                // -1 .. size-1
+                    const float ax = ix - fx, ay = iy - fy;
+                    const bool xin0 = in && x0 >= 0, xin1 = in && x0 + 1 < W, yin0 = y0 >= 0, yin1 = y0 + 1 < H;
+                    tw[jj][0] = (xin0 && yin0) ? (1.f - ax) * (1.f - ay) : 0.f; tw[jj][1] = (xin1 && yin0) ? ax * (1.f - ay) : 0.f;
+                    tw[jj][2] = (xin0 && yin1) ? (1.f - ax) * ay : 0.f;         tw[jj][3] = (xin1 && yin1) ? ax * ay : 0.f;
+                    // each footprint row is looked up at its first in-bounds pixel: (x0, y) or, for x0 == -1, (0, y); pixel 0 when unused
+                    const int first0 = y0 * W + x0 + (xin0 ? 0 : 1);
+                    rk[jj][0] = (uint32_t)((in && yin0) ? first0 : 0);
+                    rk[jj][1] = (uint32_t)((in && yin1) ? first0 + W : 0);
+                    firstx0[jj] = xin0;
+                }
+                if (a.locs_out) {
+#pragma unroll
+                    for (int jj = 0; jj < KW; jj++)
+                        if (live[jj]) reinterpret_cast<float2 *>(a.locs_out)[((size_t)(warp + NWORK * jj) * a.N + n) * HW + pofs] = make_float2(gxs[jj], gys[jj]);
+                }
+                if (D > 0) {
+                    // stage 2: ranks — one bitmap lookup per footprint row; the row's second pixel is marked too, so it is rank + 1
+                    const int rmax = D - 1;                               // defensive: a rank can never leave the table
+#pragma unroll
+                    for (int jj = 0; jj < KW; jj++)
+#pragma unroll
+                        for (int rw = 0; rw < 2; rw++) {
+                            const int pix = (int)rk[jj][rw];
+                            const int ra = (int)d.prefix[pix >> 5] + __popc(d.bitmap[pix >> 5] & ((1u << (pix & 31)) - 1u));
+                            // first pixel = x0: taps (x0, x0+1) -> ranks (ra, ra+1);  first pixel = x0+1 (x0 == -1): tap x0+1 -> rank ra
+                            rk[jj][rw] = (uint32_t)min(ra, rmax) | ((uint32_t)min(firstx0[jj] ? ra + 1 : ra, rmax) << 16);
+                        }
+                    // stage 3: interpolate the scores
+#pragma unroll
+                    for (int jj = 0; jj < KW; jj++) {
+                        float sim = tw[jj][0] * table[tix((int)(rk[jj][0] & 0xffffu), i)];
+                        sim = fmaf(tw[jj][1], table[tix((int)(rk[jj][0] >> 16), i)], sim);
+                        sim = fmaf(tw[jj][2], table[tix((int)(rk[jj][1] & 0xffffu), i)], sim);
+                        sim = fmaf(tw[jj][3], table[tix((int)(rk[jj][1] >> 16), i)], sim);
+                        x[jj] = sim;
                     }
-                    if (sim == 0.f) sim = kMasked;                      // epipolar.py:298
-                    x[jj] = sim * sl2;
+                } else {
+#pragma unroll
+                    for (int jj = 0; jj < KW; jj++) { x[jj] = 0.f; rk[jj][0] = rk[jj][1] = 0u; }
+                }
+                // ==0 mask (epipolar.py:298), scale
+#pragma unroll
+                for (int jj = 0; jj < KW; jj++) {
+                    const float sim = x[jj] == 0.f ? kMasked : x[jj];
+                    x[jj] = live[jj] ? sim * sl2 : -INFINITY;
                     mloc = fmaxf(mloc, x[jj]);
                 }
             }
