@@ -144,7 +144,8 @@ float epi_kernel_timing_last_ms(void) {
 size_t epi_fusion_cache_bytes(const EpiFusionParams *p) {
     if (!p || p->N <= 0 || p->C <= 0 || p->H <= 0 || p->W <= 0 || !want_pipe(p)) return 0;
     return align_up((size_t)p->N * 32 * sizeof(float)) + align_up((size_t)p->N * sizeof(epi::PairGeom)) +
-           align_up((size_t)p->N * p->H * p->W * sizeof(uint16_t));
+           align_up((size_t)p->N * p->H * p->W * sizeof(uint16_t)) +
+           align_up((size_t)epi::fusion_pipe_plan_records(p->N, p->H, p->W) * epi::fusion_pipe_plan_record_bytes());
 }
 
 size_t epi_fusion_workspace_bytes(const EpiFusionParams *p) {
@@ -194,6 +195,11 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
             okey = reinterpret_cast<float *>(cb);
             pg = reinterpret_cast<epi::PairGeom *>(cb + align_up((size_t)p->N * 32 * sizeof(float)));
             order = reinterpret_cast<uint16_t *>(cb + align_up((size_t)p->N * 32 * sizeof(float)) + align_up((size_t)p->N * sizeof(epi::PairGeom)));
+            if (have_P) {                      // cached work items of the fused kernel, valid per pair for the epoch stored in key slot 31
+                a.plan_cache = reinterpret_cast<uint8_t *>(order) + align_up((size_t)p->N * p->H * p->W * sizeof(uint16_t));
+                a.plan_records = epi::fusion_pipe_plan_records(p->N, p->H, p->W);
+                a.pair_epoch = reinterpret_cast<const uint32_t *>(okey) + 31;
+            }
         } else {
             order = reinterpret_cast<uint16_t *>(ws + pl.off_order);
             pg = reinterpret_cast<epi::PairGeom *>(ws + pl.off_geom);

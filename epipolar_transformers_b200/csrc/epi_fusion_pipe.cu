@@ -65,7 +65,8 @@ struct Desc {                      // one work item, written by the setup warps
     uint32_t pix[P];               // y << 16 | x, 0xFFFFFFFF = no pixel
     int tile;                      // < 0: no more work
     int n, g0, gn, D;
-    int pad[3];
+    uint32_t epoch, claim_tag;     // plan cache: valid for the pair's epoch `epoch`, built for claim `claim_tag - 1`
+    int pad[1];
 };
 constexpr uint32_t DESC_BYTES = (sizeof(Desc) + 127) / 128 * 128;
 constexpr uint32_t OFF_CTRL = OFF_DESC + NDESC * DESC_BYTES;
@@ -82,6 +83,7 @@ struct Ctrl {
     int sp;
     int cur;                       // item being built: g0 | gn << 8
     int cur_tile;
+    int cur_claim;                 // claim index of the item being built, -1 for a piece of a split tile
     int total;
     int done;
 };
@@ -135,10 +137,13 @@ using namespace pipe;
 
 #ifdef EPI_PIPE_TIMERS
 __device__ unsigned long long g_pipe_timers[32];
+__device__ long long g_pipe_trace[64 * 16];
+#define TR(item, ev) do { if (blockIdx.x == 0 && (item) < 64) g_pipe_trace[(item) * 16 + (ev)] = clock64(); } while (0)
 #define PT_DECL long long pt_prev = clock64()
 #define PT(slot) do { if (pt_on) { const long long t_ = clock64(); atomicAdd(&g_pipe_timers[slot], (unsigned long long)(t_ - pt_prev)); pt_prev = t_; } } while (0)
 #else
 #define PT_DECL do { } while (0)
+#define TR(item, ev) do { } while (0)
 #define PT(slot) do { } while (0)
 #endif
 
@@ -268,6 +273,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
             }
             named_bar(1, NT_WORK);
             PT(0);
+            if (tid == 0) TR(j, 4);
             if (tid == 0 && j >= 2) mbar_arrive(&ct.desc_free[(j - 2) % NDESC]);
             const Desc &d = desc_at(j);
             PT(1);
@@ -298,6 +304,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
             tc_fence_before();
             named_bar(1, NT_WORK);
             if (tid == 0) mbar_arrive(&ct.s_empty[j & 1]);
+            if (tid == 0) TR(j, 5);
             PT(3);
 
             // ---------------- B2a: bilinear interpolation of the scores, ==0 mask, scale ----------------
@@ -459,10 +466,12 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&ct.beta_full);
+            if (tid == 0) TR(j, 6);
             named_bar(1, NT_WORK);                          // the table is free: the epilogue transposes through it
             PT(7);
             // ---------------- epilogue of the previous item (its GEMM2 ran during this item's softmax) ----------------
             if (j >= 1) { tc_fence_after(); epilogue(j - 1); }
+            if (tid == 0) TR(j, 7);
             PT(9);
 #ifdef EPI_PIPE_TIMERS
             if (pt_on) atomicAdd(&g_pipe_timers[8], 1ull);
@@ -505,6 +514,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
         for (int j = 0;; j++) {
             Desc &d = desc_at(j);
             if (st == 0 && j >= NDESC) wait_n(&ct.desc_free[j % NDESC], (uint32_t)(j / NDESC - 1));   // the claim barrier below releases the rest
+            if (st == 0) TR(j, 0);
             PT(10);
             bool done = false;
             while (true) {
@@ -515,6 +525,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                         if (claimed == 0) c = (int)blockIdx.x;
                         else c = a.tile_counter ? (int)gridDim.x + atomicAdd(a.tile_counter, 1) : (int)blockIdx.x + claimed * (int)gridDim.x;
                         claimed++;
+                        ct.cur_claim = c;
                         // per pair: tiles [0, tpi - r_half) are claimed whole, the last r_half tiles as two halves each (the same
                         // tiles of every pair, so results do not depend on a pair's position in the batch)
                         const int whole = tiles_per_item - r_half;
@@ -525,6 +536,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                             ct.stack[0] = ((h & 1) * (P / 2)) | ((P / 2) << 8); ct.sp = 1;
                         } else ct.done = 1;
                     }
+                    else ct.cur_claim = -1;                               // a piece of a split tile: never cached
                     if (!ct.done) ct.cur = ct.stack[--ct.sp];
                 }
                 named_bar(2, NSETUP);
@@ -532,6 +544,21 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 if (ct.done) { done = true; break; }
                 const int tile = ct.cur_tile, g0 = ct.cur & 0xff, gn = ct.cur >> 8;
                 const int n = tile / tiles_per_item, trem = tile % tiles_per_item;
+                // ---- plan cache: a work item depends on the cameras only (pixel list, line end points, tap union, ranks, row list), so a
+                // claim whose record carries the pair's current epoch is copied instead of rebuilt (records live in the caller's cache) ----
+                const int claim = ct.cur_claim;                            // >= 0 only for a freshly claimed (unsplit) item
+                uint8_t *rec = (a.plan_cache && !a.locs_in && claim >= 0 && claim < a.plan_records) ? a.plan_cache + (size_t)claim * DESC_BYTES : nullptr;
+                const uint32_t ep = rec ? __ldg(a.pair_epoch + 32 * n) : 0u;
+                if (rec) {
+                    const Desc *g = reinterpret_cast<const Desc *>(rec);
+                    if (g->epoch == ep && g->claim_tag == (uint32_t)claim + 1u && g->tile == tile) {      // uniform: every thread reads the same words
+                        const uint4 *src4 = reinterpret_cast<const uint4 *>(rec);
+                        uint4 *dst4 = reinterpret_cast<uint4 *>(&d);
+                        for (int q = st; q < (int)(sizeof(Desc) / 16); q += NSETUP) dst4[q] = src4[q];
+                        named_bar(2, NSETUP);
+                        break;
+                    }
+                }
                 if (st < P) {                               // pixel + its epipolar line end points
                     const int e = trem * P + st;
                     unsigned p = 0u;
@@ -614,8 +641,13 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 named_bar(2, NSETUP);
                 PT(17);
                 if (st < 16 && Dc > 0) { const int r = Dc + st; if (r < ((Dc + 15) & ~15)) d.idx[r] = d.idx[0]; }
-                if (st == 16) d.D = Dc;
+                if (st == 16) { d.D = Dc; d.epoch = ep; d.claim_tag = (uint32_t)claim + 1u; }
                 named_bar(2, NSETUP);
+                if (rec && D <= DMAX) {                                   // publish the record (read by later launches only)
+                    const uint4 *src4 = reinterpret_cast<const uint4 *>(&d);
+                    uint4 *dst4 = reinterpret_cast<uint4 *>(rec);
+                    for (int q = st; q < (int)(sizeof(Desc) / 16); q += NSETUP) dst4[q] = src4[q];
+                }
                 PT(18);
                 break;
             }
@@ -624,6 +656,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 break;
             }
             if (st == 0) mbar_arrive(&ct.desc_full[j % NDESC]);
+            if (st == 0) TR(j, 1);
             PT(11);
         }
     } else if (warp < W_MMA) {
@@ -750,8 +783,10 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     }
                 }
             }
+            if (gt == 0) TR(j, 2);
             if (j >= 1) {
                 if (desc_at(j - 1).D > 0) gemm2_stages(j - 1);
+                if (gt == 0) TR(j - 1, 8);
                 named_bar(3, NGATHER);                      // every gather thread has read item j-1's row list
                 if (gt == 0) mbar_arrive(&ct.desc_free[(j - 1) % NDESC]);
             }
@@ -801,6 +836,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     }
             }
             if (lane == 0) mma_commit(&ct.o_full[jj & 1]);
+            if (lane == 0) TR(jj, 9);
             __syncwarp();
         };
         for (int j = 0;; j++) {
@@ -846,6 +882,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     qcount++;
                 }
                 if (lane == 0) mma_commit(&ct.s_full[j & 1]);
+                if (lane == 0) TR(j, 3);
                 __syncwarp();
             }
             if (j >= 1) gemm2(j - 1);
@@ -861,11 +898,16 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
 
 
 #ifdef EPI_PIPE_TIMERS
+extern "C" void epi_pipe_trace_read(long long *out1024) { cudaMemcpyFromSymbol(out1024, g_pipe_trace, sizeof(long long) * 64 * 16); }
 extern "C" void epi_pipe_timers_read(unsigned long long *out32, int reset) {
     cudaMemcpyFromSymbol(out32, g_pipe_timers, sizeof(unsigned long long) * 32);
     if (reset) { unsigned long long z[32] = {0}; cudaMemcpyToSymbol(g_pipe_timers, z, sizeof(z)); }
 }
 #endif
+
+size_t fusion_pipe_plan_record_bytes() { return DESC_BYTES; }
+// claims = whole tiles + the half items of the last partial round over the grid (< number of SMs, rounded up per pair)
+int fusion_pipe_plan_records(int N, int H, int W) { return N * ((H * W + P - 1) / P) + 256 + N; }
 
 bool fusion_pipe_shape_ok(int C, int H, int W, int K, bool has_locs_in) {
     if (C % 8 != 0 || C > 256 || C < 8) return false;

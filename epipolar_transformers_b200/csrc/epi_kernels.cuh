@@ -24,6 +24,9 @@ struct FusionArgs {
     int *tile_counter;                        // zeroed by the staging kernel; dynamic tile scheduler of the tile kernel
     const PairGeom *pair_geom;                // [N] per-pair constants (fp64-derived) written by the staging kernel — pipe kernel
     int *err_flag;                            // device word OR-ed with 1 when a work item had to be dropped (never for supported shapes)
+    uint8_t *plan_cache;                      // optional persistent records of the pipe kernel's work items (camera-only data), or null
+    int plan_records;                         // capacity of plan_cache in records of fusion_pipe_plan_record_bytes()
+    const uint32_t *pair_epoch;               // [N] stride 32 words: epoch of each pair's cached plan (bumped by the staging kernel on a key miss)
     GeomCfg geom;
 };
 
@@ -71,6 +74,8 @@ cudaError_t launch_fusion_warp(const FusionArgs &a, cudaStream_t st);
 cudaError_t launch_fusion_tile(const FusionArgs &a, cudaStream_t st);
 cudaError_t launch_fusion_pipe(const FusionArgs &a, cudaStream_t st);
 bool fusion_pipe_shape_ok(int C, int H, int W, int K, bool has_locs_in);
+size_t fusion_pipe_plan_record_bytes();
+int fusion_pipe_plan_records(int N, int H, int W);
 bool fusion_tile_supported(const FusionArgs &a);
 bool fusion_tile_shape_ok(int C, int H, int W, int K, bool has_locs_in);
 cudaError_t launch_sector_order(const float *P_ref, const float *P_src, uint16_t *order, int N, const GeomCfg &gc, cudaStream_t st);

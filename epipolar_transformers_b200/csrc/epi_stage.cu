@@ -101,8 +101,11 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
             else if (t == 26) my_key = s.gc.ds;
             else if (t == 27) my_key = s.gc.r;
             else if (t == 28) my_key = 1.f;                      // valid marker (a zero-initialised cache never matches)
+            else if (t == 29) my_key = (float)(s.gc.K + 1024 * s.gc.correct + 2048 * s.gc.align);
+            else if (t == 30) my_key = s.gc.eps;
+            // slot 31 = epoch of this pair's cached plan (bumped on every miss; read by the fused kernel), not part of the comparison
             if (s.order_key) {
-                const bool same = __float_as_uint(s.order_key[32 * n + t]) == __float_as_uint(my_key);
+                const bool same = t == 31 || __float_as_uint(s.order_key[32 * n + t]) == __float_as_uint(my_key);
                 if (__all_sync(0xffffffffu, same)) s_e[7] = 1.f; else s_e[7] = 0.f;
             } else s_e[7] = 0.f;
         }
@@ -238,7 +241,8 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
         }
         if (s.order_key) {                                       // publish the key last (same stream => ordered for the next call)
             __syncthreads();
-            if (t < 32) s.order_key[32 * n + t] = my_key;
+            if (t < 31) s.order_key[32 * n + t] = my_key;
+            else if (t == 31) reinterpret_cast<uint32_t *>(s.order_key)[32 * n + 31] += 1u;   // invalidates the pair's cached work items
         }
         return;
     }

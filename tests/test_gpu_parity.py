@@ -262,6 +262,27 @@ def test_fused_caller_residual_module():
         assert same[0] is t1 and same[1] is None
 
 
+@pytest.mark.parametrize("name", ["cfg1_ring", "tiny_ring_z", "cfg2_r50_256_randn"])
+def test_persistent_cache_is_transparent(name):
+    """FusionState (persistent workspace + camera-keyed cache of pixel order, pair constants and the fused kernel's work
+    items): miss, hit, changed cameras, and back — every call must equal the stateless call bit for bit."""
+    cfg, f1, f2, P1, P2, params = gc.build_inputs(name)
+    spec = gc.CASES[name]
+    kw = dict(K=spec["K"], downsample=cfg.BACKBONE.DOWNSAMPLE, img_scale=cfg.DATASETS.IMAGE_RESIZE * cfg.DATASETS.PREDICT_RESIZE,
+              softmax_scale=cfg.EPIPOLAR.SOFTMAXSCALE, correct_normalize=spec["correct"], want_locs=True)
+    if params:
+        kw.update(z_folded=fold_params(params, spec["zres"]), z_residual=spec["zres"])
+    t1, t2 = dev(f1), dev(f2)
+    PA = (dev(P1), dev(P2))
+    PB = (dev(P1[::-1].copy()), dev(P2[::-1].copy()))               # other cameras in every batch slot
+    want = {k: epi.epipolar_fusion(t1, t2, *P, **kw) for k, P in (("A", PA), ("B", PB))}
+    state = epi.FusionState()
+    for which in ("A", "A", "B", "B", "A"):                          # miss, hit, miss (epoch bump), hit, miss
+        got = epi.epipolar_fusion(t1, t2, *(PA if which == "A" else PB), state=state, **kw)
+        for g, w in zip(got, want[which]):
+            assert torch.equal(g, w), which
+
+
 def test_errors_are_loud():
     cfg = epi.make_cfg(EPIPOLAR=dict(ATTENTION="max"))
     with pytest.raises(NotImplementedError):

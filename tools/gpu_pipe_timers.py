@@ -16,8 +16,9 @@ f1 = torch.relu(torch.randn(N, C, H, W, device="cuda")); f2 = torch.relu(torch.r
 P1 = torch.from_numpy(P1.astype(np.float32)).cuda(); P2 = torch.from_numpy(P2.astype(np.float32)).cuda()
 wf = torch.randn(C, C, device="cuda") * 0.05; bf = torch.randn(C, device="cuda")
 buf = (ctypes.c_ulonglong * 32)()
+state = epi.FusionState() if "--nocache" not in sys.argv else None
 for it in range(3):
-    epi.epipolar_fusion(f1, f2, P1, P2, K=K, correct_normalize=True, variant="pipe", z_folded=(wf, bf), z_residual=True)
+    epi.epipolar_fusion(f1, f2, P1, P2, K=K, correct_normalize=True, variant="pipe", z_folded=(wf, bf), z_residual=True, state=state)
     torch.cuda.synchronize()
     lib.epi_pipe_timers_read(buf, 1)
 v = np.array(list(buf), dtype=np.float64)
@@ -35,3 +36,15 @@ for lo, hi, nm in ((0, 8, "workers(excl epi)"), (10, 12, "setup(part)"), (13, 17
 sb = (ctypes.c_ulonglong * 16)()
 lib.epi_stage_timers_read(sb)
 print("stage order block (cycles): geom+zero %d, hist %d, scan %d, place %d, binsort %d" % tuple(list(sb)[:5]))
+
+# ---- timeline of CTA 0 (clock64, relative to the first event) ----
+tr = (ctypes.c_longlong * 1024)()
+lib.epi_pipe_trace_read(tr)
+t = np.array(list(tr), dtype=np.int64).reshape(64, 16)
+ev = ["setup start", "desc ready", "G1 gathers issued", "G1 mma issued", "workers start", "B1 done", "beta ready", "iter end (epi j-1)", "G2 gathers issued", "G2 mma issued"]
+t0 = t[0, 0]
+print("timeline of CTA 0 (kcycles since its first setup start):")
+print("item " + " ".join("%11s" % e[:11] for e in ev))
+for j in range(8):
+    if t[j, 0] == 0 and j > 0: break
+    print("%4d " % j + " ".join("%11.1f" % ((t[j, e] - t0) / 1e3) if t[j, e] else "%11s" % "-" for e in range(10)))
