@@ -277,8 +277,10 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
         }
         return;
     }
+    // reference and source tiles alternate in block order: when the source map is a peer-mapped tensor of another GPU its
+    // NVLink reads (~0.77 TB/s, microsecond latency) overlap the local reference tiles instead of queueing behind them
     int map = 0;
-    if (s.do_ref && s.do_src) { map = lin >= per_map; lin -= map * per_map; }
+    if (s.do_ref && s.do_src) { map = lin & 1; lin >>= 1; }
     else map = s.do_src ? 1 : 0;
     const int n = lin / (tiles_p * tiles_c), rem = lin % (tiles_p * tiles_c);
     const int c0 = (rem / tiles_p) * TC, p0 = (rem % tiles_p) * TPX;
