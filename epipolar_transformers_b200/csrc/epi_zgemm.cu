@@ -71,7 +71,7 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
     if (tid == 0) {
         auto load = [&](int q) {
             uint8_t *st = smem + (q & 1) * STAGE;
-            mbar_arrive_expect_tx(&bars[q & 1], 2 * A_PLANE + 2 * B_PLANE);
+            mbar_arrive_expect_tx(&bars[q & 1], 2 * A_PLANE + 2 * (uint32_t)(C < 256 ? C : 256) * 128u);   // W box = min(C, 256) rows x 128 B
             tma_load_2d(st, &tm_hi, q * 64, n * HW + p0, &bars[q & 1]);
             tma_load_2d(st + A_PLANE, &tm_lo, q * 64, n * HW + p0, &bars[q & 1]);
             tma_load_2d(st + 2 * A_PLANE, &tw_hi, q * 64, 0, &bars[q & 1]);

@@ -240,6 +240,25 @@ def test_module_contract_and_state_dict():
     assert rel_max(out_tr.cpu().numpy(), ref_tr.detach().cpu().numpy()) < 1e-3
 
 
+@pytest.mark.parametrize("C", [64, 128, 192])
+def test_z_epilogue_tensor_core_channel_counts(C):
+    """z conv + BN(eval) + ZRESIDUAL on the tensor-core GEMM for every supported channel count (weight box = C rows)."""
+    from epipolar_transformers_b200 import synthetic as syn
+    N, H, W, K = 2, 24, 24, 16
+    cfg = epi.make_cfg(KEYPOINT=dict(HEATMAP_SIZE=(H, W), NFEATS=C),
+                       EPIPOLAR=dict(SAMPLESIZE=K, USE_CORRECT_NORMALIZE=True, PARAMETERIZED=("z",), ZRESIDUAL=True))
+    P1, P2 = syn.pairs_from_ring(N, 4 * H)
+    P1, P2 = P1.astype(np.float32), P2.astype(np.float32)
+    f1, f2 = syn.features(N, C, H, W, "randn", 21), syn.features(N, C, H, W, "randn", 22)
+    params = syn.z_bn_params(C, 5)
+    out, corr, attn, locs = epi.epipolar_fusion(dev(f1), dev(f2), dev(P1), dev(P2), K=K, correct_normalize=True, want_locs=True,
+                                                z_folded=fold_params(params, True), z_residual=True, add_ref_residual=True)
+    torch.cuda.synchronize()
+    o = c_oracle.forward(cfg, f1, f2, P1, P2, locs=locs.cpu().numpy())
+    want = eo.z_epilogue(o["out"], params, True) + f1
+    assert rel_max(out.cpu().numpy(), want) < TOL
+
+
 def test_fused_caller_residual_module():
     """Epipolar(fuse_ref_residual=True) + fused_other_feat == the reference caller's `ret + feat`
     (modeling/backbones/resnet.py:377-388), with and without the z epilogue; other_features=None passes feat through."""

@@ -3,10 +3,11 @@ import csv, json, os, subprocess, sys
 from collections import defaultdict
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-TAG = sys.argv[1] if len(sys.argv) > 1 else "r1"
+TAG = sys.argv[1] if len(sys.argv) > 1 else "r2"
 GO, PR = os.path.join(ROOT, "gpurun_out"), os.path.join(ROOT, "profiles")
 os.makedirs(PR, exist_ok=True)
-KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__cycles_active", "gpu__dram_throughput",
+KEYS = ["gpu__time_duration.sum", "smsp__issue_active.avg", "sm__inst_executed.avg.per_cycle_elapsed", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum", "smsp__average_warps_issue_stalled", "dram__bytes_read.sum", "dram__bytes_write.sum", "dram__cycles_active", "gpu__dram_throughput",
         "sm__pipe_tensor_cycles_active", "sm__warps_active", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "l1tex__t_bytes.sum", "smsp__inst_executed.sum",
         "sm__cycles_elapsed.max", "lts__t_sector_hit_rate", "sm__inst_executed_pipe_tensor", "launch__shared_mem_per_block"]
@@ -33,8 +34,8 @@ shutil.copy(lp, os.path.join(PR, "launches_%s.csv" % TAG))
 
 # 2. full captures -> selected raw metrics
 traffic = {}
-for name in ("tile", "zgemm", "split"):
-    rep = os.path.join(GO, "prof_%s_%s.ncu-rep" % (name, TAG))
+for name, kern in (("pipe", "epi_fusion_pipe"), ("zgemm", "epi_zgemm"), ("stage", "epi_stage")):
+    rep = os.path.join(GO, "prof_%s_%s.ncu-rep" % (kern, TAG))
     if not os.path.exists(rep):
         continue
     out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -54,6 +55,6 @@ for name in ("tile", "zgemm", "split"):
 if traffic:
     tp = os.path.join(PR, "traffic.json")
     cur = json.load(open(tp)) if os.path.exists(tp) else {}
-    cur["cfg2"] = {"dram_bytes_per_launch": traffic.get("tile"), "by_kernel": traffic, "tag": TAG}
+    cur["cfg2"] = {"dram_bytes_per_launch": traffic.get("pipe"), "by_kernel": traffic, "step_total": sum(traffic.values()), "tag": TAG}
     json.dump(cur, open(tp, "w"), indent=1)
 print(open(os.path.join(PR, "launches_%s.md" % TAG)).read()); print(traffic)
