@@ -913,9 +913,12 @@ bool fusion_pipe_shape_ok(int C, int H, int W, int K, bool has_locs_in) {
     if (C % 8 != 0 || C > 256 || C < 8) return false;
     if (H * W > MAXWORDS * 32 || H * W > 65535) return false;
     if (K > 32 * MAXKPL) return false;
-    // a single pixel's union must fit DMAX: 4 taps per sample, and (fused geometry) a straight line crosses at most
-    // H+W pixel rows/columns, 2 pixels wide, plus the footprint ends
-    const int single = has_locs_in ? 4 * K : (4 * K < 2 * (H + W) + 8 ? 4 * K : 2 * (H + W) + 8);
+    // A single pixel's union must fit DMAX (items are split down to one pixel).  4 taps per sample; and for the fused geometry the
+    // samples lie on a straight segment: along its dominant axis it crosses at most max(W, H) columns, and a column u belongs to the
+    // footprint of samples with ix in [u-1, u+1) — over that interval iy moves by at most 2, so floor(iy) takes at most 3 values and
+    // the 2-row footprints cover at most 4 rows: the union has at most 4 * max(W, H) pixels.
+    const int mx = H > W ? H : W;
+    const int single = has_locs_in ? 4 * K : (4 * K < 4 * mx ? 4 * K : 4 * mx);
     return single <= DMAX;
 }
 
