@@ -138,4 +138,26 @@ __device__ __forceinline__ Taps make_taps(float gx, float gy, int H, int W, int 
     return t;
 }
 
+
+// Programmatic dependent launch (the three launches of a forward are chained with
+// cudaLaunchAttributeProgrammaticStreamSerialization): a kernel's CTAs may become resident and run their prologue
+// (barrier init, TMEM allocation, tensor-map prefetch) while the previous kernel of the stream drains;
+// pdl_wait() returns once that kernel has completed and its writes are visible.  Nothing the previous kernels
+// wrote may be read, and nothing they read may be written, before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#endif
+
 }  // namespace epi

@@ -165,11 +165,19 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
     const int nwords = (HW + 31) >> 5;
     const int NH = (C + 127) >> 7;                  // channel halves of 128 (GEMM2 M)
     const int NP = (C + 63) >> 6;                   // 64-channel panels
+    // C > 256 ("wide"): the query panels are loaded in two halves of four (GEMM1 accumulates over both), the fused-feature
+    // accumulator takes all 256 columns of the O region (four channel halves, single-buffered) and the epilogue runs twice.
+    const bool wide = C > 256;
+    const int NQH = wide ? 2 : 1;
+    auto obuf = [&](int jj) -> int { return wide ? 0 : (jj & 1); };                 // O accumulator buffer of item jj
+    auto ouse = [&](int jj) -> uint32_t { return (uint32_t)(wide ? jj : (jj >> 1)); };   // earlier uses of that buffer
+    auto ocol = [&](int jj, int h) -> uint32_t { return TMEM_O + (wide ? 0u : (uint32_t)(jj & 1) * 128u) + (uint32_t)h * 64u; };
     const GeomCfg gc = a.geom;
     const int NHW = a.N * HW;                       // plane stride (rows) of the operand buffer [ref_hi|ref_lo|src_hi|src_lo]
     constexpr int KW = 2 * KPL;                     // samples per worker warp (k = warp + 16 jj)
 
-    // ---------------- one-time setup ----------------
+    // ---------------- one-time setup (overlaps the staging launch's tail: programmatic dependent launch) ----------------
+    pdl_launch_dependents();
     if (warp == 0) tmem_alloc(&ct.tmem_base, TMEM_COLS);
     if (tid == 32) {
         for (int i = 0; i < NDESC; i++) { mbar_init(&ct.desc_full[i], 1); mbar_init(&ct.desc_free[i], 2); }
@@ -187,6 +195,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = ct.tmem_base;
+    pdl_wait();                                     // operand planes, pixel order, pair constants, counters: the staging launch
 
     if (warp < NWORK) {
         // =====================================================================================================
@@ -209,52 +218,56 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
         // epilogue of item j (accumulator buffer j & 1): fused feature TMEM -> table (as [pixel][channel]) -> global
         auto epilogue = [&](int j) {
             const Desc &d = desc_at(j);
-            {
-                const int h = (warp >> 2) & 1, ph = warp >> 3;
-                const int c = h * 128 + (warp & 3) * 32 + lane;
-                if (h < NH) {
-                    float v[16], v2[16];
-                    const uint32_t col = TMEM_O + (uint32_t)(j & 1) * 128u + (uint32_t)h * 64u + (uint32_t)ph * 16u;
-                    tmem_ld_32x16(tmem + tq + col, v);
-                    tmem_ld_32x16(tmem + tq + col + 32u, v2);
-                    tmem_ld_wait();
+            const int nparts = wide ? 2 : 1;
+            for (int part = 0; part < nparts; part++) {
+                if (part) named_bar(1, NT_WORK);            // the first 256 channels have left the table
+                {
+                    const int h = (warp >> 2) & 1, ph = warp >> 3;
+                    const int c = h * 128 + (warp & 3) * 32 + lane;
+                    if (part * 2 + h < NH) {
+                        float v[16], v2[16];
+                        const uint32_t col = ocol(j, part * 2 + h) + (uint32_t)ph * 16u;
+                        tmem_ld_32x16(tmem + tq + col, v);
+                        tmem_ld_32x16(tmem + tq + col + 32u, v2);
+                        tmem_ld_wait();
 #pragma unroll
-                    for (int ii = 0; ii < 16; ii++) table[(ph * 16 + ii) * 256 + c] = d.D > 0 ? v[ii] + v2[ii] : 0.f;   // D == 0: all masked
+                        for (int ii = 0; ii < 16; ii++) table[(ph * 16 + ii) * 256 + c] = d.D > 0 ? v[ii] + v2[ii] : 0.f;   // D == 0: all masked
+                    }
                 }
-            }
-            tc_fence_before();
-            named_bar(1, NT_WORK);
-            if (lane == 0 && warp < NWORK) mbar_arrive(&ct.o_empty[j & 1]);
+                tc_fence_before();
+                named_bar(1, NT_WORK);
+                if (part == nparts - 1 && lane == 0) mbar_arrive(&ct.o_empty[obuf(j)]);
 #pragma unroll
-            for (int u = 0; u < 2; u++) {
-                const int i = warp * 2 + u;
-                const uint32_t p = d.pix[i];
-                if (i < d.g0 || i >= d.g0 + d.gn || p == 0xFFFFFFFFu) continue;          // warp-uniform
-                const int y = (int)(p >> 16), x = (int)(p & 0xffffu);
+                for (int u = 0; u < 2; u++) {
+                    const int i = warp * 2 + u;
+                    const uint32_t p = d.pix[i];
+                    if (i < d.g0 || i >= d.g0 + d.gn || p == 0xFFFFFFFFu) continue;          // warp-uniform
+                    const int y = (int)(p >> 16), x = (int)(p & 0xffffu);
 #pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    const int c0 = hh * 128 + lane * 4;
-                    if (c0 >= C) continue;
-                    const float4 o = *reinterpret_cast<const float4 *>(table + i * 256 + c0);
-                    if (a.out_hi) {
-                        const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
-                        const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
-                        const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
-                        const size_t off = ((size_t)d.n * HW + y * W + x) * C + c0;
-                        *reinterpret_cast<uint2 *>(a.out_hi + off) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
-                        *reinterpret_cast<uint2 *>(a.out_lo + off) = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
-                    } else if (a.out_stride[1] == 1 && !a.add_ref) {
-                        // channel-contiguous output (channels_last, or the library's pixel-major plane): one 16-byte store per lane
-                        *reinterpret_cast<float4 *>(a.out + (int64_t)d.n * a.out_stride[0] + (int64_t)y * a.out_stride[2] + (int64_t)x * a.out_stride[3] + c0) = o;
-                    } else {
-                        const float ov[4] = {o.x, o.y, o.z, o.w};
-                        float *ob = a.out + (int64_t)d.n * a.out_stride[0] + (int64_t)y * a.out_stride[2] + (int64_t)x * a.out_stride[3];
-                        const float *rb = a.feat_ref + (int64_t)d.n * a.ref_stride[0] + (int64_t)y * a.ref_stride[2] + (int64_t)x * a.ref_stride[3];
+                    for (int hh = 0; hh < 2; hh++) {
+                        const int ct0 = hh * 128 + lane * 4, c0 = part * 256 + ct0;
+                        if (c0 >= C) continue;
+                        const float4 o = *reinterpret_cast<const float4 *>(table + i * 256 + ct0);
+                        if (a.out_hi) {
+                            const __nv_bfloat162 h0 = __floats2bfloat162_rn(o.x, o.y), h1 = __floats2bfloat162_rn(o.z, o.w);
+                            const float2 f0 = __bfloat1622float2(h0), f1 = __bfloat1622float2(h1);
+                            const __nv_bfloat162 l0 = __floats2bfloat162_rn(o.x - f0.x, o.y - f0.y), l1 = __floats2bfloat162_rn(o.z - f1.x, o.w - f1.y);
+                            const size_t off = ((size_t)d.n * HW + y * W + x) * C + c0;
+                            *reinterpret_cast<uint2 *>(a.out_hi + off) = make_uint2(*reinterpret_cast<const uint32_t *>(&h0), *reinterpret_cast<const uint32_t *>(&h1));
+                            *reinterpret_cast<uint2 *>(a.out_lo + off) = make_uint2(*reinterpret_cast<const uint32_t *>(&l0), *reinterpret_cast<const uint32_t *>(&l1));
+                        } else if (a.out_stride[1] == 1 && !a.add_ref) {
+                            // channel-contiguous output (channels_last, or the library's pixel-major plane): one 16-byte store per lane
+                            *reinterpret_cast<float4 *>(a.out + (int64_t)d.n * a.out_stride[0] + (int64_t)y * a.out_stride[2] + (int64_t)x * a.out_stride[3] + c0) = o;
+                        } else {
+                            const float ov[4] = {o.x, o.y, o.z, o.w};
+                            float *ob = a.out + (int64_t)d.n * a.out_stride[0] + (int64_t)y * a.out_stride[2] + (int64_t)x * a.out_stride[3];
+                            const float *rb = a.feat_ref + (int64_t)d.n * a.ref_stride[0] + (int64_t)y * a.ref_stride[2] + (int64_t)x * a.ref_stride[3];
 #pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            float val = ov[e];
-                            if (a.add_ref) val += __ldg(rb + (int64_t)(c0 + e) * a.ref_stride[1]);
-                            ob[(int64_t)(c0 + e) * a.out_stride[1]] = val;
+                            for (int e = 0; e < 4; e++) {
+                                float val = ov[e];
+                                if (a.add_ref) val += __ldg(rb + (int64_t)(c0 + e) * a.ref_stride[1]);
+                                ob[(int64_t)(c0 + e) * a.out_stride[1]] = val;
+                            }
                         }
                     }
                 }
@@ -428,7 +441,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 }
             }
             if (a.corr_pos) { red_bv[warp * 32 + lane] = best_v; red_bk[warp * 32 + lane] = best_k; }
-            if (warp == 0 && j >= 1) wait_n(&ct.o_full[(j - 1) & 1], (uint32_t)((j - 1) >> 1));   // GEMM2(j-1) has consumed the β panels
+            if (warp == 0 && j >= 1) wait_n(&ct.o_full[obuf(j - 1)], ouse(j - 1));   // GEMM2(j-1) has consumed the β panels
             named_bar(1, NT_WORK);
             PT(5);
             // ---------------- arg-max -> corr_pos (first maximum, like torch.argmax) ----------------
@@ -478,7 +491,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
 #endif
         }
         if (j >= 1) {                                   // drain
-            if (warp == 0) wait_n(&ct.o_full[(j - 1) & 1], (uint32_t)((j - 1) >> 1));
+            if (warp == 0) wait_n(&ct.o_full[obuf(j - 1)], ouse(j - 1));
             named_bar(1, NT_WORK);
             tc_fence_after();
             epilogue(j - 1);
@@ -729,57 +742,60 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
             const Desc &d = desc_at(j);
             const bool last = d.tile < 0;
             if (!last && d.D > 0) {
-                // ---- query rows of the item's pixels: stacked panels [hi 32 rows | lo 32 rows] x NP ----
-                if (qcount >= 1) {
-                    if (gt < 32) wait_n(&ct.q_empty, qcount - 1);
-                    named_bar(3, NGATHER);
-                }
-                PT(16);
-                {
-                    const __nv_bfloat16 *ref = planes + (size_t)d.n * HW * C;
+                // ---- per half of the query panels (one half unless C > 256): the item's query rows as stacked panels
+                //      [hi 32 rows | lo 32 rows], then the GEMM1 stages (chunk, 64-channel panel) that multiply with them ----
+                const int D16 = (d.D + 15) & ~15, nch = (d.D + CHUNK - 1) / CHUNK;
+                const __nv_bfloat16 *src = planes + 2 * plane_elems + (size_t)d.n * HW * C;
+                for (int qh = 0; qh < NQH; qh++) {
+                    const int npq = min(4, NP - qh * 4);
+                    if (qcount >= 1) {
+                        if (gt < 32) wait_n(&ct.q_empty, qcount - 1);
+                        named_bar(3, NGATHER);
+                    }
+                    PT(16);
+                    {
+                        const __nv_bfloat16 *ref = planes + (size_t)d.n * HW * C;
 #pragma unroll
-                    for (int it = 0; it < 2; it++) {
-                        const int r = gr + 16 * it;
-                        const uint32_t p = d.pix[r];
-                        const __nv_bfloat16 *row = ref + (size_t)(p == 0xFFFFFFFFu ? 0 : (int)(p >> 16) * W + (int)(p & 0xffffu)) * C;
-                        const uint32_t so = smem_base + OFF_Q + so0 + (uint32_t)it * 2048u;
+                        for (int it = 0; it < 2; it++) {
+                            const int r = gr + 16 * it;
+                            const uint32_t p = d.pix[r];
+                            const __nv_bfloat16 *row = ref + (size_t)(p == 0xFFFFFFFFu ? 0 : (int)(p >> 16) * W + (int)(p & 0xffffu)) * C;
+                            const uint32_t so = smem_base + OFF_Q + so0 + (uint32_t)it * 2048u;
 #pragma unroll
-                        for (int kp = 0; kp < 4; kp++) {
-                            const int ch = kp * 64 + gj * 8;
-                            if (kp < NP) {                  // channels beyond C are zero-filled: they are part of the MMA K range
-                                const bool ok = ch < C;
-                                cp16(so + kp * PANEL_B2, ok ? row + ch : row, ok);
-                                cp16(so + kp * PANEL_B2 + 4096, ok ? row + plane_elems + ch : row, ok);
+                            for (int kp = 0; kp < 4; kp++) {
+                                const int ch = (qh * 4 + kp) * 64 + gj * 8;
+                                if (kp < npq) {                 // channels beyond C are zero-filled: they are part of the MMA K range
+                                    const bool ok = ch < C;
+                                    cp16(so + kp * PANEL_B2, ok ? row + ch : row, ok);
+                                    cp16(so + kp * PANEL_B2 + 4096, ok ? row + plane_elems + ch : row, ok);
+                                }
                             }
                         }
                     }
-                }
-                arrive_async(&ct.q_full);
-                qcount++;
-                // ---- GEMM1 stages: (chunk, 64-channel panel); the row addresses of a chunk are computed once for its NP panels ----
-                const int D16 = (d.D + 15) & ~15, nch = (d.D + CHUNK - 1) / CHUNK;
-                const __nv_bfloat16 *src = planes + 2 * plane_elems + (size_t)d.n * HW * C;
-                for (int c = 0; c < nch; c++) {
-                    const int rows = min(CHUNK, D16 - c * CHUNK);
-                    uint32_t roff[8];
+                    arrive_async(&ct.q_full);
+                    qcount++;
+                    for (int c = 0; c < nch; c++) {             // the row addresses of a chunk are computed once for its panels
+                        const int rows = min(CHUNK, D16 - c * CHUNK);
+                        uint32_t roff[8];
 #pragma unroll
-                    for (int it = 0; it < 8; it++) roff[it] = (gr + 16 * it < rows) ? (uint32_t)d.idx[c * CHUNK + gr + 16 * it] * (uint32_t)C : 0u;
-                    for (int kp = 0; kp < NP; kp++) {
-                        const uint32_t stg = smem_base + (uint32_t)(stage_acquire() - smem);
-                        const int ch = kp * 64 + gj * 8;
-                        const bool ok = ch < C;
-                        const __nv_bfloat16 *colp = src + (ok ? ch : 0);
+                        for (int it = 0; it < 8; it++) roff[it] = (gr + 16 * it < rows) ? (uint32_t)d.idx[c * CHUNK + gr + 16 * it] * (uint32_t)C : 0u;
+                        for (int kp = 0; kp < npq; kp++) {
+                            const uint32_t stg = smem_base + (uint32_t)(stage_acquire() - smem);
+                            const int ch = (qh * 4 + kp) * 64 + gj * 8;
+                            const bool ok = ch < C;
+                            const __nv_bfloat16 *colp = src + (ok ? ch : 0);
 #pragma unroll
-                        for (int it = 0; it < 8; it++) {
-                            if (gr + 16 * it < rows) {
-                                const __nv_bfloat16 *row = colp + roff[it];
-                                const uint32_t so = stg + so0 + (uint32_t)it * 2048u;
-                                cp16(so, row, ok);
-                                cp16(so + PLANE_BYTES, row + plane_elems, ok);
+                            for (int it = 0; it < 8; it++) {
+                                if (gr + 16 * it < rows) {
+                                    const __nv_bfloat16 *row = colp + roff[it];
+                                    const uint32_t so = stg + so0 + (uint32_t)it * 2048u;
+                                    cp16(so, row, ok);
+                                    cp16(so + PLANE_BYTES, row + plane_elems, ok);
+                                }
                             }
+                            arrive_async(&ct.f_full[fcount % NSTAGE]);
+                            fcount++;
                         }
-                        arrive_async(&ct.f_full[fcount % NSTAGE]);
-                        fcount++;
                     }
                 }
             }
@@ -805,7 +821,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
             PT(20);
             wait_n(&ct.beta_full, (uint32_t)jj);
             PT(21);
-            if (jj >= 2) wait_n(&ct.o_empty[jj & 1], (uint32_t)((jj >> 1) - 1));
+            if (jj >= (wide ? 1 : 2)) wait_n(&ct.o_empty[obuf(jj)], ouse(jj) - 1u);
             PT(22);
             tc_fence_after();
             if (d.D > 0) {
@@ -821,7 +837,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                         tc_fence_after();
                         if (lane == 0) {
                             const uint32_t sa = smem_u32(smem + OFF_STAGE + s * STAGE_BYTES);
-                            const uint32_t dst = tmem + TMEM_O + (uint32_t)(jj & 1) * 128u + (uint32_t)h * 64u;
+                            const uint32_t dst = tmem + ocol(jj, h);
                             const int nk = min(4, (D16 - blk * 64) >> 4);
                             for (int kk = 0; kk < nk; kk++) {
                                 const uint64_t a_hi = make_smem_desc(sa + kk * 2048, 8192, 1024), a_lo = make_smem_desc(sa + PLANE_BYTES + kk * 2048, 8192, 1024);
@@ -835,7 +851,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                         fcount++;
                     }
             }
-            if (lane == 0) mma_commit(&ct.o_full[jj & 1]);
+            if (lane == 0) mma_commit(&ct.o_full[obuf(jj)]);
             if (lane == 0) TR(jj, 9);
             __syncwarp();
         };
@@ -850,36 +866,41 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 PT(25);
                 tc_fence_after();
                 if (d.D > 0) {
-                    wait_n(&ct.q_full, qcount);
-                    PT(26);
-                    fence_proxy_async_smem();
                     const int nch = (d.D + CHUNK - 1) / CHUNK;
                     const uint32_t idesc64 = make_idesc_bf16(128, 2 * P, 0, 0), idesc32 = make_idesc_bf16(128, P, 0, 0);
-                    for (int c = 0; c < nch; c++)
-                        for (int kp = 0; kp < NP; kp++) {
-                            const uint32_t s = fcount % NSTAGE;
-                            PT(20);
-                            wait_n(&ct.f_full[s], fcount / NSTAGE);
-                            PT(27);
-                            fence_proxy_async_smem();
-                            tc_fence_after();
-                            if (lane == 0) {
-                                const uint32_t sa = smem_u32(smem + OFF_STAGE + s * STAGE_BYTES);
-                                const uint32_t dst = tmem + TMEM_S + (uint32_t)(j & 1) * 128u + (uint32_t)c * 64u;
+                    for (int qh = 0; qh < NQH; qh++) {
+                        const int npq = min(4, NP - qh * 4);
+                        PT(20);
+                        wait_n(&ct.q_full, qcount);
+                        PT(26);
+                        fence_proxy_async_smem();
+                        for (int c = 0; c < nch; c++)
+                            for (int kp = 0; kp < npq; kp++) {
+                                const uint32_t s = fcount % NSTAGE;
+                                PT(20);
+                                wait_n(&ct.f_full[s], fcount / NSTAGE);
+                                PT(27);
+                                fence_proxy_async_smem();
+                                tc_fence_after();
+                                if (lane == 0) {
+                                    const uint32_t sa = smem_u32(smem + OFF_STAGE + s * STAGE_BYTES);
+                                    const uint32_t dst = tmem + TMEM_S + (uint32_t)(j & 1) * 128u + (uint32_t)c * 64u;
 #pragma unroll
-                                for (int ks = 0; ks < 4; ks++) {
-                                    const uint64_t a_hi = make_smem_desc(sa + ks * 32, 16, 1024), a_lo = make_smem_desc(sa + PLANE_BYTES + ks * 32, 16, 1024);
-                                    const uint64_t b = make_smem_desc(sq + kp * PANEL_B2 + ks * 32, 16, 1024);
-                                    mma_bf16(dst, a_hi, b, idesc64, (kp | ks) ? 1u : 0u);      // [F_hi·Q_hi | F_hi·Q_lo]
-                                    mma_bf16(dst, a_lo, b, idesc32, 1u);                      //  += F_lo·Q_hi
+                                    for (int ks = 0; ks < 4; ks++) {
+                                        const uint64_t a_hi = make_smem_desc(sa + ks * 32, 16, 1024), a_lo = make_smem_desc(sa + PLANE_BYTES + ks * 32, 16, 1024);
+                                        const uint64_t b = make_smem_desc(sq + kp * PANEL_B2 + ks * 32, 16, 1024);
+                                        mma_bf16(dst, a_hi, b, idesc64, (qh | kp | ks) ? 1u : 0u);      // [F_hi·Q_hi | F_hi·Q_lo]
+                                        mma_bf16(dst, a_lo, b, idesc32, 1u);                           //  += F_lo·Q_hi
+                                    }
+                                    mma_commit(&ct.f_empty[s]);
                                 }
-                                mma_commit(&ct.f_empty[s]);
+                                __syncwarp();
+                                fcount++;
                             }
-                            __syncwarp();
-                            fcount++;
-                        }
-                    if (lane == 0) mma_commit(&ct.q_empty);
-                    qcount++;
+                        if (lane == 0) mma_commit(&ct.q_empty);
+                        __syncwarp();
+                        qcount++;
+                    }
                 }
                 if (lane == 0) mma_commit(&ct.s_full[j & 1]);
                 if (lane == 0) TR(j, 3);
@@ -910,7 +931,7 @@ size_t fusion_pipe_plan_record_bytes() { return DESC_BYTES; }
 int fusion_pipe_plan_records(int N, int H, int W) { return N * ((H * W + P - 1) / P) + 256 + N; }
 
 bool fusion_pipe_shape_ok(int C, int H, int W, int K, bool has_locs_in) {
-    if (C % 8 != 0 || C > 256 || C < 8) return false;
+    if (C % 8 != 0 || C > 512 || C < 8) return false;
     if (H * W > MAXWORDS * 32 || H * W > 65535) return false;
     if (K > 32 * MAXKPL) return false;
     // A single pixel's union must fit DMAX (items are split down to one pixel).  4 taps per sample; and for the fused geometry the
@@ -942,7 +963,8 @@ cudaError_t launch_fusion_pipe(const FusionArgs &a, cudaStream_t st) {
         if (sms_cached <= 0) sms_cached = 148;
     }
     const int grid = tiles < sms_cached ? tiles : sms_cached;      // one persistent CTA per SM
-    kern<<<grid, NT_ALL, SMEM_ALLOC, st>>>(a);
+    cudaError_t le = launch_pdl(kern, dim3((unsigned)grid), dim3(NT_ALL), (size_t)SMEM_ALLOC, st, a);
+    if (le != cudaSuccess) return le;
     return cudaGetLastError();
 }
 

@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
     const int t = threadIdx.x;
     const int H = s.H, W = s.W, HW = H * W, C = s.C;
     const int nord = s.do_order ? s.N : 0;
+    pdl_launch_dependents();                               // the fused kernel's CTAs may start their prologue as SMs drain
+    pdl_wait();                                            // previous forward's kernels (they read what this launch rewrites)
     if (blockIdx.x == 0 && t == 0 && s.zero_words) { s.zero_words[0] = 0; s.zero_words[1] = 0; }
 
     if ((int)blockIdx.x < nord) {
@@ -368,8 +370,7 @@ cudaError_t launch_stage(const float *ref, const int64_t ref_stride[4], const fl
         if (e != cudaSuccess) return e;
         smem_set = smem;
     }
-    epi_stage_kernel<<<grid, stg::NT, smem, st>>>(s);
-    return cudaGetLastError();
+    return launch_pdl(epi_stage_kernel, dim3((unsigned)grid), dim3(stg::NT), smem, st, s);
 }
 
 }  // namespace epi

@@ -4,7 +4,8 @@
 // restates  finalout = bn(z(out)) [+ out]   /root/reference/modeling/layers/epipolar.py:249-253 (eval-mode BN folded
 // into Wf, bf by epi_fold_z_bn_f32) and  ret + feat   /root/reference/modeling/backbones/resnet.py:388.
 //
-// One CTA per 128 pixels: D[128 px, C out] = X[128 px, C]·Wfᵀ with X supplied by the fusion kernel as bf16
+// One CTA per 128 pixels and block of up to 256 output channels (blockIdx.y; two blocks when 256 < C <= 512):
+// D[128 px, C out] = X[128 px, C]·Wfᵀ with X supplied by the fusion kernel as bf16
 // (hi, lo) planes [N·HW, C] (K-major rows) and Wf split to (hi, lo) while it is staged.  Three MMAs per
 // product (hi·hi + hi·lo + lo·hi), fp32 accumulation in TMEM (M=128, N=C<=256), K streamed in 64-channel
 // panels through a double-buffered shared-memory ring — the X panels arrive by TMA (cp.async.bulk.tensor.2d with the
@@ -51,8 +52,11 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
     const int tiles = (HW + 127) / 128;
     const int n = blockIdx.x / tiles, p0 = (blockIdx.x % tiles) * 128;
     const int nq = (C + 63) / 64;                      // K panels of 64 channels
+    const int oc0 = (int)blockIdx.y * 256;            // this CTA's block of output channels
+    const int CO = min(256, C - oc0);
     const __nv_bfloat16 *xh = z.x_hi + (size_t)n * HW * C, *xl = z.x_lo + (size_t)n * HW * C;
 
+    pdl_launch_dependents();
     if (warp == 0) tmem_alloc(tmem_slot, 256);
     if (tid == 32) { for (int i = 0; i < 5; i++) mbar_init(&bars[i], 1); mbar_fence_init(); }
     if (tid == 64) {
@@ -65,6 +69,7 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    pdl_wait();                                        // the fused kernel's feature planes
 
     // One thread drives the whole main loop: TMA loads of the (A, W) panels into a 2-stage ring, tcgen05.mma issue, commits.
     // A: 128 pixel rows x 64 channels of the (hi, lo) planes of x;  B: C output rows x 64 input channels of the (hi, lo) planes of Wf.
@@ -74,12 +79,12 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
             mbar_arrive_expect_tx(&bars[q & 1], 2 * A_PLANE + 2 * (uint32_t)(C < 256 ? C : 256) * 128u);   // W box = min(C, 256) rows x 128 B
             tma_load_2d(st, &tm_hi, q * 64, n * HW + p0, &bars[q & 1]);
             tma_load_2d(st + A_PLANE, &tm_lo, q * 64, n * HW + p0, &bars[q & 1]);
-            tma_load_2d(st + 2 * A_PLANE, &tw_hi, q * 64, 0, &bars[q & 1]);
-            tma_load_2d(st + 2 * A_PLANE + B_PLANE, &tw_lo, q * 64, 0, &bars[q & 1]);
+            tma_load_2d(st + 2 * A_PLANE, &tw_hi, q * 64, oc0, &bars[q & 1]);
+            tma_load_2d(st + 2 * A_PLANE + B_PLANE, &tw_lo, q * 64, oc0, &bars[q & 1]);
         };
         load(0);
         if (nq > 1) load(1);
-        const uint32_t idesc = make_idesc_bf16(128, z.Npad, 0, 0);
+        const uint32_t idesc = make_idesc_bf16(128, (uint32_t)((CO + 15) & ~15), 0, 0);
         for (int q = 0; q < nq; q++) {
             const uint32_t buf = q & 1;
             for (uint32_t it = 0; !mbar_try_wait(&bars[buf], (q >> 1) & 1); ++it) if (it > (1u << 24)) __trap();
@@ -113,13 +118,13 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
     constexpr int OT = 132;
     {
         const int r = (warp & 3) * 32 + lane;
-        for (int cb = (warp >> 2) * 32; cb < C; cb += 128) {
+        for (int cb = (warp >> 2) * 32; cb < CO; cb += 128) {
             float v[32];
             tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + cb, v);
             tmem_ld_wait();
 #pragma unroll
             for (int jj = 0; jj < 32; jj++)
-                if (cb + jj < C) otile[(cb + jj) * OT + r] = v[jj];
+                if (cb + jj < CO) otile[(cb + jj) * OT + r] = v[jj];
         }
     }
     tc_fence_before();
@@ -131,8 +136,9 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
                          (!addr || ((z.ref_stride[3] == 1) && (z.ref_stride[2] == W) && (z.ref_stride[1] % 4 == 0) && (z.ref_stride[0] % 4 == 0) &&
                                     ((reinterpret_cast<uintptr_t>(z.ref) & 15) == 0)));
         const int pp = lane * 4, p = p0 + pp;
-        for (int o = warp; o < C; o += NT / 32) {
-            const float4 t = *reinterpret_cast<const float4 *>(otile + o * OT + pp);
+        for (int ol = warp; ol < CO; ol += NT / 32) {
+            const int o = oc0 + ol;
+            const float4 t = *reinterpret_cast<const float4 *>(otile + ol * OT + pp);
             const float b = __ldg(z.bf + o);
             float y[4] = {t.x + b, t.y + b, t.z + b, t.w + b};
             if (vec && p + 3 < HW) {
@@ -156,7 +162,7 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
     if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-bool zgemm_supported(int C) { return C % 64 == 0 && C >= 64 && C <= 256; }   // whole 64-channel TMA panels
+bool zgemm_supported(int C) { return C % 64 == 0 && C >= 64 && C <= 512; }   // whole 64-channel TMA panels; two output blocks above 256
 
 namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -203,8 +209,7 @@ cudaError_t launch_zgemm(const ZGemmArgs &z, cudaStream_t st) {
             return cudaErrorInvalidValue;
         mc.xh = z.x_hi; mc.wh = z.w_hi; mc.rows = z.N * z.HW; mc.C = z.C;
     }
-    epi_zgemm_kernel<<<z.N * tiles, zg::NT, zg::SMEM_ALLOC, st>>>(z, mc.m[0], mc.m[1], mc.m[2], mc.m[3]);
-    return cudaGetLastError();
+    return launch_pdl(epi_zgemm_kernel, dim3((unsigned)(z.N * tiles), (unsigned)((z.C + 255) / 256)), dim3(zg::NT), (size_t)zg::SMEM_ALLOC, st, z, mc.m[0], mc.m[1], mc.m[2], mc.m[3]);
 }
 
 }  // namespace epi

@@ -240,9 +240,10 @@ def test_module_contract_and_state_dict():
     assert rel_max(out_tr.cpu().numpy(), ref_tr.detach().cpu().numpy()) < 1e-3
 
 
-@pytest.mark.parametrize("C", [64, 128, 192])
+@pytest.mark.parametrize("C", [64, 128, 192, 320, 512])
 def test_z_epilogue_tensor_core_channel_counts(C):
-    """z conv + BN(eval) + ZRESIDUAL on the tensor-core GEMM for every supported channel count (weight box = C rows)."""
+    """z conv + BN(eval) + ZRESIDUAL on the tensor-core GEMM for every supported channel count (weight box = min(C, 256) rows;
+    two blocks of output channels above 256) behind the pipelined kernel (forced: an unsupported shape would be EINVAL)."""
     from epipolar_transformers_b200 import synthetic as syn
     N, H, W, K = 2, 24, 24, 16
     cfg = epi.make_cfg(KEYPOINT=dict(HEATMAP_SIZE=(H, W), NFEATS=C),
@@ -252,7 +253,7 @@ def test_z_epilogue_tensor_core_channel_counts(C):
     f1, f2 = syn.features(N, C, H, W, "randn", 21), syn.features(N, C, H, W, "randn", 22)
     params = syn.z_bn_params(C, 5)
     out, corr, attn, locs = epi.epipolar_fusion(dev(f1), dev(f2), dev(P1), dev(P2), K=K, correct_normalize=True, want_locs=True,
-                                                z_folded=fold_params(params, True), z_residual=True, add_ref_residual=True)
+                                                z_folded=fold_params(params, True), z_residual=True, add_ref_residual=True, variant="pipe")
     torch.cuda.synchronize()
     o = c_oracle.forward(cfg, f1, f2, P1, P2, locs=locs.cpu().numpy())
     want = eo.z_epilogue(o["out"], params, True) + f1
@@ -373,8 +374,10 @@ def test_host_streamer_matches_direct_call():
         assert torch.equal(o, out.cpu()) and torch.equal(a_, attn.cpu()) and torch.equal(c, corr.cpu())
 
 
+PIPE_MAX_HW = 16384
 SWEEP = [  # (N, C, H, W, K)   BASELINE config 5 corners + map sizes on both sides of the tensor-core kernel's limits
-    (1, 64, 64, 64, 16), (1, 128, 64, 64, 32), (1, 256, 64, 64, 128), (1, 512, 32, 32, 64),   # C=512 -> warp kernel
+    (1, 64, 64, 64, 16), (1, 128, 64, 64, 32), (1, 256, 64, 64, 128), (1, 512, 32, 32, 64),   # C=512: two query-panel halves
+    (2, 512, 64, 64, 128), (1, 384, 48, 40, 32), (1, 264, 40, 40, 16),                         # wide corners, C % 64 != 0 above 256
     (1, 64, 128, 128, 32),                                                                       # H*W = 16384: largest tile-kernel map
     (1, 32, 160, 96, 16),                                                                        # non-square
     (1, 16, 144, 144, 16),                                                                       # H*W > 16384 -> warp kernel
@@ -392,7 +395,11 @@ def test_sweep_shapes_vs_oracle(shape):
     P1, P2 = syn.pairs_from_ring(max(N, 2), 4 * max(H, W), seed=K)
     P1, P2 = P1[:N].astype(np.float32), P2[:N].astype(np.float32)
     f1 = syn.features(N, C, H, W, "randn", 5); f2 = syn.features(N, C, H, W, "randn", 6)
-    out, corr, attn, locs = epi.epipolar_fusion(dev(f1), dev(f2), dev(P1), dev(P2), K=K, correct_normalize=True, want_locs=True)
+    # the documented limits of the pipelined tensor-core kernel: inside them the kernel is FORCED, so a shape
+    # that silently fell back to another kernel would fail with EINVAL instead of passing
+    pipe_ok = C % 8 == 0 and 8 <= C <= 512 and H * W <= PIPE_MAX_HW and K <= 128 and min(4 * K, 4 * max(H, W)) <= 256
+    out, corr, attn, locs = epi.epipolar_fusion(dev(f1), dev(f2), dev(P1), dev(P2), K=K, correct_normalize=True, want_locs=True,
+                                                variant="pipe" if pipe_ok else "auto")
     torch.cuda.synchronize()
     o = c_oracle.forward(cfg, f1, f2, P1, P2, locs=locs.cpu().numpy())
     assert rel_max(out.cpu().numpy(), o["out"]) < TOL
