@@ -210,7 +210,7 @@ int epi_fusion_forward_f32(const EpiFusionParams *p, void *stream) {
         e = epi::launch_stage(p->feat_ref, p->ref_stride, p->feat_src, p->src_stride, planes, p->P_ref, p->P_src, pg, order, okey,
                               z_planes ? p->z_weight_folded : nullptr, wpl, p->z_residual ? 1 : 0, words, p->N, p->C, p->H, p->W, a.geom, st);
         if (e != cudaSuccess) return fail(EPI_ECUDA, "operand staging launch failed: %s", cudaGetErrorString(e));
-        launches++;
+        launches += (order && (size_t)p->H * p->W * 2 + 16384 > 64 * 1024) ? 2 : 1;      // large maps order their pixels in a launch of their own
         w_hi = wpl; w_lo = wpl ? wpl + (size_t)p->C * p->C : nullptr;
         a.ref_hi = planes; a.ref_lo = planes + elems; a.src_hi = planes + 2 * elems; a.src_lo = planes + 3 * elems;
         a.order = order; a.pair_geom = pg; a.tile_counter = words; a.err_flag = words + 1;

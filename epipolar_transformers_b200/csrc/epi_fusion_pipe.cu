@@ -69,6 +69,18 @@ struct Desc {                      // one work item, written by the setup warps
     int pad[1];
 };
 constexpr uint32_t DESC_BYTES = (sizeof(Desc) + 127) / 128 * 128;
+
+// Maps above 16384 pixels (up to 256 rows x 1024 columns) do not fit a one-bit-per-pixel bitmap in the descriptor.  Their items
+// re-use the same 3 KB (bitmap + prefix) as a ROW-WINDOWED bitmap: per source row a mask of the 32-pixel words the union touches,
+// and only those words are stored, in (row, word) order — at most one word per union pixel, so WIN_WORDS = DMAX always suffices.
+//   rank(x, y) = prefix[w] + popc(bitmap[w] & below(x % 32)),   w = wbase[y] + popc(rowmask[y] & below(x / 32))
+constexpr int WIN_WORDS = 256, WIN_ROWS = 256, WIN_MAXW = 1024;
+struct WinView { uint32_t *bitmap, *rowmask; uint16_t *prefix, *wbase; };
+__device__ __forceinline__ WinView win_view(Desc &d) {
+    uint8_t *b = reinterpret_cast<uint8_t *>(d.bitmap);
+    return {reinterpret_cast<uint32_t *>(b), reinterpret_cast<uint32_t *>(b + 1024), reinterpret_cast<uint16_t *>(b + 2048), reinterpret_cast<uint16_t *>(b + 2560)};
+}
+static_assert(sizeof(uint32_t) * MAXWORDS + sizeof(uint16_t) * MAXWORDS >= 4 * WIN_WORDS + 4 * WIN_ROWS + 2 * WIN_WORDS + 2 * WIN_ROWS, "windowed view fits");
 constexpr uint32_t OFF_CTRL = OFF_DESC + NDESC * DESC_BYTES;
 
 struct Ctrl {
@@ -163,6 +175,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
     const int r_half = min(tiles_per_item, (tail_tiles + a.N - 1) / a.N);          // per pair
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nwords = (HW + 31) >> 5;
+    const bool big = nwords > MAXWORDS;             // row-windowed union bitmap (see WinView)
     const int NH = (C + 127) >> 7;                  // channel halves of 128 (GEMM2 M)
     const int NP = (C + 63) >> 6;                   // 64-channel panels
     // C > 256 ("wide"): the query panels are loaded in two halves of four (GEMM1 accumulates over both), the fused-feature
@@ -361,8 +374,14 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     tw[jj][2] = (xin0 && yin1) ? (1.f - ax) * ay : 0.f;         tw[jj][3] = (xin1 && yin1) ? ax * ay : 0.f;
                     // each footprint row is looked up at its first in-bounds pixel: (x0, y) or, for x0 == -1, (0, y); pixel 0 when unused
                     const int first0 = y0 * W + x0 + (xin0 ? 0 : 1);
-                    rk[jj][0] = (uint32_t)((in && yin0) ? first0 : 0);
-                    rk[jj][1] = (uint32_t)((in && yin1) ? first0 + W : 0);
+                    if (!big) {
+                        rk[jj][0] = (uint32_t)((in && yin0) ? first0 : 0);
+                        rk[jj][1] = (uint32_t)((in && yin1) ? first0 + W : 0);
+                    } else {                                    // windowed bitmap: row << 16 | column
+                        const uint32_t xf = (uint32_t)(x0 + (xin0 ? 0 : 1));
+                        rk[jj][0] = (in && yin0) ? ((uint32_t)y0 << 16 | xf) : 0u;
+                        rk[jj][1] = (in && yin1) ? ((uint32_t)(y0 + 1) << 16 | xf) : 0u;
+                    }
                     firstx0[jj] = xin0;
                 }
                 if (a.locs_out) {
@@ -371,6 +390,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                         if (live[jj]) reinterpret_cast<float2 *>(a.locs_out)[((size_t)(warp + NWORK * jj) * a.N + n) * HW + pofs] = make_float2(gxs[jj], gys[jj]);
                 }
                 if (D > 0) {
+                    const WinView wv = win_view(const_cast<Desc &>(d));
                     // stage 2: ranks — one bitmap lookup per footprint row; the row's second pixel is marked too, so it is rank + 1
                     const int rmax = D - 1;                               // defensive: a rank can never leave the table
 #pragma unroll
@@ -378,7 +398,13 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
 #pragma unroll
                         for (int rw = 0; rw < 2; rw++) {
                             const int pix = (int)rk[jj][rw];
-                            const int ra = (int)d.prefix[pix >> 5] + __popc(d.bitmap[pix >> 5] & ((1u << (pix & 31)) - 1u));
+                            int ra;
+                            if (!big) ra = (int)d.prefix[pix >> 5] + __popc(d.bitmap[pix >> 5] & ((1u << (pix & 31)) - 1u));
+                            else {
+                                const int yy = pix >> 16, xx = pix & 0xffff;
+                                const int wi = min((int)wv.wbase[yy] + __popc(wv.rowmask[yy] & ((1u << (xx >> 5)) - 1u)), WIN_WORDS - 1);
+                                ra = (int)wv.prefix[wi] + __popc(wv.bitmap[wi] & ((1u << (xx & 31)) - 1u));
+                            }
                             // first pixel = x0: taps (x0, x0+1) -> ranks (ra, ra+1);  first pixel = x0+1 (x0 == -1): tap x0+1 -> rank ra
                             rk[jj][rw] = (uint32_t)min(ra, rmax) | ((uint32_t)min(firstx0[jj] ? ra + 1 : ra, rmax) << 16);
                         }
@@ -510,10 +536,15 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
         for (int jj = 0; jj < KPL; jj++) tk[jj] = (float)(lane + 32 * jj) / (float)(K - 1);
         // every in-bounds pixel of the 2x2 bilinear footprint (a superset of the taps with non-zero weight): one atomicOr per
         // footprint row (two only when the row's pixels straddle a 32-bit word)
-        auto mark = [&](Desc &d, float gx, float gy) {
+        auto footprint = [&](float gx, float gy, int &x0, int &y0) -> bool {
             const float ix = grid2pix(gx, W, gc.align), iy = grid2pix(gy, H, gc.align);
-            if (!(ix > -1.f && ix < (float)W && iy > -1.f && iy < (float)H)) return;       // also rejects NaN / far sentinels
-            const int x0 = (int)floorf(ix), y0 = (int)floorf(iy);                          // -1 .. size-1
+            if (!(ix > -1.f && ix < (float)W && iy > -1.f && iy < (float)H)) return false;    // also rejects NaN / far sentinels
+            x0 = (int)floorf(ix); y0 = (int)floorf(iy);                                       // -1 .. size-1
+            return true;
+        };
+        auto mark = [&](Desc &d, float gx, float gy) {
+            int x0, y0;
+            if (!footprint(gx, gy, x0, y0)) return;
             const uint32_t mbits = x0 < 0 ? 1u : (x0 + 1 < W ? 3u : 1u);                   // pixels max(x0,0) [, x0+1]
             const int pos = y0 * W + max(x0, 0);
             auto row = [&](int ps) {
@@ -523,6 +554,66 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
             };
             if (y0 >= 0) row(pos);
             if (y0 + 1 < H) row(pos + W);
+        };
+        // row-windowed variant, pass A: which 32-pixel words of each source row the union touches
+        auto mark_rows = [&](const WinView &wv, float gx, float gy) {
+            int x0, y0;
+            if (!footprint(gx, gy, x0, y0)) return;
+            const int xa = max(x0, 0), xb = min(x0 + 1, W - 1);
+            const uint32_t m = (1u << (xa >> 5)) | (1u << (xb >> 5));
+            if (y0 >= 0) atomicOr(&wv.rowmask[y0], m);
+            if (y0 + 1 < H) atomicOr(&wv.rowmask[y0 + 1], m);
+        };
+        // pass B: the pixels, into the compacted words
+        auto mark_bits = [&](const WinView &wv, float gx, float gy) {
+            int x0, y0;
+            if (!footprint(gx, gy, x0, y0)) return;
+            const int xa = max(x0, 0), xb = min(x0 + 1, W - 1);
+            auto row = [&](int y) {
+                const uint32_t rm = wv.rowmask[y];
+                const int wa = min((int)wv.wbase[y] + __popc(rm & ((1u << (xa >> 5)) - 1u)), WIN_WORDS - 1);
+                if ((xa >> 5) == (xb >> 5)) atomicOr(&wv.bitmap[wa], (1u << (xa & 31)) | (1u << (xb & 31)));
+                else { atomicOr(&wv.bitmap[wa], 1u << 31); atomicOr(&wv.bitmap[min(wa + 1, WIN_WORDS - 1)], 1u); }
+            };
+            if (y0 >= 0) row(y0);
+            if (y0 + 1 < H) row(y0 + 1);
+        };
+        // every (pixel, sample) location of the group [g0, g0 + gn): lane <-> sample
+        auto for_each_loc = [&](Desc &d, int n, int g0, int gn, auto &&fn) {
+            for (int i = g0 + sw; i < g0 + gn; i += NSETUP / 32) {
+                const uint32_t p = d.pix[i];
+                if (p == 0xFFFFFFFFu) continue;
+                if (a.locs_in) {
+#pragma unroll
+                    for (int jj = 0; jj < KPL; jj++) {
+                        const int k = lane + 32 * jj;
+                        if (k < K) {
+                            const float2 l = __ldg(reinterpret_cast<const float2 *>(a.locs_in) + ((size_t)k * a.N + n) * HW + (p >> 16) * W + (p & 0xffffu));
+                            fn(l.x, l.y);
+                        }
+                    }
+                } else {
+                    const float4 e = d.ends[i];
+#pragma unroll
+                    for (int jj = 0; jj < KPL; jj++)
+                        if (lane + 32 * jj < K) fn(img2grid_x(lerp_exact(e.x, e.z, tk[jj]), gc), img2grid_y(lerp_exact(e.y, e.w, tk[jj]), gc));
+                }
+            }
+        };
+        // exclusive prefix of the popcounts of `nw` words by the first setup warp; leaves the total in ct.total
+        auto prefix_words = [&](const uint32_t *bm, uint16_t *pf, int nw) {
+            const int per = (nw + 31) >> 5;
+            int cnt = 0;
+            for (int q = 0; q < per; q++) { const int w = lane * per + q; if (w < nw) cnt += __popc(bm[w]); }
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
+            int run = incl - cnt;
+            for (int q = 0; q < per; q++) {
+                const int w = lane * per + q;
+                if (w < nw) { pf[w] = (uint16_t)run; run += __popc(bm[w]); }
+            }
+            if (lane == 31) ct.total = incl;
         };
         for (int j = 0;; j++) {
             Desc &d = desc_at(j);
@@ -589,46 +680,31 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     }
                     d.ends[st] = en;
                 } else if (st == P) { d.tile = tile; d.n = n; d.g0 = g0; d.gn = gn; }
-                for (int w = st - 64; w >= 0 && w < nwords; w += 64) d.bitmap[w] = 0u;     // warps 2,3 clear the bitmap
+                for (int w = st - 64; w >= 0 && w < (big ? 2 * WIN_WORDS : nwords); w += 64) d.bitmap[w] = 0u;     // warps 2,3 clear the bitmap (+ row masks)
                 named_bar(2, NSETUP);
                 PT(29);
                 // ---- union of the in-bounds taps: lane <-> sample (consecutive samples fall into different words) ----
-                for (int i = g0 + sw; i < g0 + gn; i += NSETUP / 32) {
-                    const uint32_t p = d.pix[i];
-                    if (p == 0xFFFFFFFFu) continue;
-                    if (a.locs_in) {
-#pragma unroll
-                        for (int jj = 0; jj < KPL; jj++) {
-                            const int k = lane + 32 * jj;
-                            if (k < K) {
-                                const float2 l = __ldg(reinterpret_cast<const float2 *>(a.locs_in) + ((size_t)k * a.N + n) * HW + (p >> 16) * W + (p & 0xffffu));
-                                mark(d, l.x, l.y);
-                            }
-                        }
-                    } else {
-                        const float4 e = d.ends[i];
-#pragma unroll
-                        for (int jj = 0; jj < KPL; jj++)
-                            if (lane + 32 * jj < K)
-                                mark(d, img2grid_x(lerp_exact(e.x, e.z, tk[jj]), gc), img2grid_y(lerp_exact(e.y, e.w, tk[jj]), gc));
-                    }
-                }
-                named_bar(2, NSETUP);
-                PT(30);
-                // ---- exclusive prefix of popcounts (first setup warp; 16 words per lane max) ----
-                if (sw == 0) {
-                    const int per = (nwords + 31) >> 5;
-                    int cnt = 0;
-                    for (int q = 0; q < per; q++) { const int w = lane * per + q; if (w < nwords) cnt += __popc(d.bitmap[w]); }
-                    int incl = cnt;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += v; }
-                    int run = incl - cnt;
-                    for (int q = 0; q < per; q++) {
-                        const int w = lane * per + q;
-                        if (w < nwords) { d.prefix[w] = (uint16_t)run; run += __popc(d.bitmap[w]); }
-                    }
-                    if (lane == 31) ct.total = incl;
+                const WinView wv = win_view(d);
+                bool too_wide = false;
+                if (!big) {
+                    for_each_loc(d, n, g0, gn, [&](float gx, float gy) { mark(d, gx, gy); });
+                    named_bar(2, NSETUP);
+                    PT(30);
+                    if (sw == 0) prefix_words(d.bitmap, d.prefix, nwords);
+                } else {
+                    for_each_loc(d, n, g0, gn, [&](float gx, float gy) { mark_rows(wv, gx, gy); });
+                    named_bar(2, NSETUP);
+                    if (sw == 0) prefix_words(wv.rowmask, wv.wbase, H);             // wbase[y] = words before row y
+                    named_bar(2, NSETUP);
+                    const int TW = ct.total;
+                    named_bar(2, NSETUP);                                            // ct.total is rewritten below
+                    too_wide = TW > WIN_WORDS;                                        // more touched words than union rows allowed: split
+                    if (!too_wide) {
+                        for_each_loc(d, n, g0, gn, [&](float gx, float gy) { mark_bits(wv, gx, gy); });
+                        named_bar(2, NSETUP);
+                        PT(30);
+                        if (sw == 0) prefix_words(wv.bitmap, wv.prefix, TW);
+                    } else if (st == 0) ct.total = DMAX + 1;
                 }
                 named_bar(2, NSETUP);
                 PT(31);
@@ -645,11 +721,23 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 const int Dc = D > DMAX ? 0 : D;          // a single pixel over DMAX cannot happen for supported shapes (host check)
                 if (D > DMAX && st == 0 && a.err_flag) atomicOr(a.err_flag, 1);
                 // ---- union list: idx[rank] = source pixel; pad to a multiple of 16 with a valid row ----
-                if (Dc > 0)
+                if (Dc > 0 && !big)
                     for (int w = st; w < nwords; w += NSETUP) {
                         uint32_t bits = d.bitmap[w];
                         int r = d.prefix[w];
                         while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; d.idx[r++] = (uint16_t)(w * 32 + b); }
+                    }
+                if (Dc > 0 && big)
+                    for (int y = st; y < H; y += NSETUP) {
+                        uint32_t rm = wv.rowmask[y];
+                        int wi = wv.wbase[y];
+                        while (rm) {
+                            const int xw = __ffs(rm) - 1; rm &= rm - 1;
+                            uint32_t bits = wv.bitmap[wi];
+                            int r = wv.prefix[wi];
+                            while (bits) { const int b = __ffs(bits) - 1; bits &= bits - 1; d.idx[r++] = (uint16_t)(y * W + xw * 32 + b); }
+                            wi++;
+                        }
                     }
                 named_bar(2, NSETUP);
                 PT(17);
@@ -932,7 +1020,7 @@ int fusion_pipe_plan_records(int N, int H, int W) { return N * ((H * W + P - 1) 
 
 bool fusion_pipe_shape_ok(int C, int H, int W, int K, bool has_locs_in) {
     if (C % 8 != 0 || C > 512 || C < 8) return false;
-    if (H * W > MAXWORDS * 32 || H * W > 65535) return false;
+    if (H * W > MAXWORDS * 32 && (H > WIN_ROWS || W > WIN_MAXW || H * W > 65536)) return false;   // row-windowed bitmap above 16384 pixels
     if (K > 32 * MAXKPL) return false;
     // A single pixel's union must fit DMAX (items are split down to one pixel).  4 taps per sample; and for the fused geometry the
     // samples lie on a straight segment: along its dominant axis it crosses at most max(W, H) columns, and a column u belongs to the

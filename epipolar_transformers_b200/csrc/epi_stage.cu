@@ -160,22 +160,34 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
         ST(0);
         const float ex = s_e[0], ey = s_e[1], cdx = s_e[2], cdy = s_e[3], klo = s_e[5], kinv = s_e[6];
         const bool parallel = s_e[4] != 0.f;
-        // bins of this thread's pixels (i = t + 256 m), kept in registers between the two passes
-        constexpr int MAXPT = 64;                                        // H*W <= 16384
+        // bins of this thread's pixels (i = t + 256 m), kept in registers between the two passes (maps up to 16384 pixels; larger
+        // maps recompute the key in the placement pass — the order is cached per camera pair, so this runs once per rig)
+        constexpr int MAXPT = 64;
         const int npt = (HW - t + NT - 1) / NT;
+        const bool keep = npt <= MAXPT;
         uint16_t bins[MAXPT];
-        {
+        auto bin_of = [&](int x, int y) -> int {
+            return (int)(angle_key(pix2coord(x, s.gc.ds, s.gc.r), pix2coord(y, s.gc.ds, s.gc.r), ex, ey, cdx, cdy, parallel, klo, kinv) * (float)NBIN);
+        };
+        const int sx = NT % W, sy = NT / W;
+        if (keep) {
             int x = t % W, y = t / W;
-            const int sx = NT % W, sy = NT / W;
 #pragma unroll 4
             for (int m = 0; m < MAXPT; m++) {
                 if (m < npt) {
-                    const int b = (int)(angle_key(pix2coord(x, s.gc.ds, s.gc.r), pix2coord(y, s.gc.ds, s.gc.r), ex, ey, cdx, cdy, parallel, klo, kinv) * (float)NBIN);
+                    const int b = bin_of(x, y);
                     bins[m] = (uint16_t)b;
                     atomicAdd(&hist[b], 1);
                     x += sx; y += sy;
                     if (x >= W) { x -= W; y++; }
                 }
+            }
+        } else {
+            int x = t % W, y = t / W;
+            for (int m = 0; m < npt; m++) {
+                atomicAdd(&hist[bin_of(x, y)], 1);
+                x += sx; y += sy;
+                if (x >= W) { x -= W; y++; }
             }
         }
         __syncthreads();
@@ -199,9 +211,18 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
         __syncthreads();
         ST(2);
         // placement (arbitrary order inside a bin) into the shared list
+        if (keep) {
 #pragma unroll 4
-        for (int m = 0; m < MAXPT; m++)
-            if (m < npt) lst[atomicAdd(&hist[bins[m]], 1)] = (uint16_t)(t + NT * m);
+            for (int m = 0; m < MAXPT; m++)
+                if (m < npt) lst[atomicAdd(&hist[bins[m]], 1)] = (uint16_t)(t + NT * m);
+        } else {
+            int x = t % W, y = t / W;
+            for (int m = 0; m < npt; m++) {
+                lst[atomicAdd(&hist[bin_of(x, y)], 1)] = (uint16_t)(t + NT * m);
+                x += sx; y += sy;
+                if (x >= W) { x -= W; y++; }
+            }
+        }
         __syncthreads();
         ST(3);
         // inside every bin: ascending pixel index (in-place insertion sort; bins hold ~HW/4096 entries)
@@ -211,10 +232,12 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
 #pragma unroll
             for (int q = 0; q < PER; q++) {
                 const int len = loc[q];
-                if (len > SMALL) {
+                bool coop = false;                          // long bins are ranked by the whole block below (64 of them at most)
+                if (len > (keep ? SMALL : 4 * SMALL)) {
                     const int slot = atomicAdd(&s_nbig, 1);
-                    if (slot < 64) s_big[slot] = t * PER + q;
-                } else {
+                    if (slot < 64) { s_big[slot] = t * PER + q; coop = true; }
+                }
+                if (!coop) {
                     for (int e = 1; e < len; e++) {
                         const uint16_t xv = lst[st0 + e];
                         int p = e;
@@ -360,16 +383,33 @@ cudaError_t launch_stage(const float *ref, const int64_t ref_stride[4], const fl
     s.do_ref = 1; s.do_src = 1; s.do_order = (P_ref && P_src && order) ? 1 : 0;
     const int tiles = ((H * W + stg::TPX - 1) / stg::TPX) * ((C + stg::TC - 1) / stg::TC) * N;
     const int wblocks = (Wf && w_planes) ? (C * C / 8 + stg::NT - 1) / stg::NT : 0;        // C % 8 == 0
-    const int grid = (s.do_order ? N : 0) + 2 * tiles + wblocks;
     // dynamic shared memory: the transposition tile, or (order blocks) 16 KB histogram + 2 B per pixel
-    size_t smem = (size_t)stg::TC * stg::TPITCH * sizeof(float);
-    if (s.do_order && (size_t)stg::NBIN * 4 + (size_t)H * W * 2 > smem) smem = (size_t)stg::NBIN * 4 + (size_t)H * W * 2;
+    const size_t smem_tile = (size_t)stg::TC * stg::TPITCH * sizeof(float);
+    const size_t smem_order = (size_t)stg::NBIN * 4 + (size_t)H * W * 2;
     static thread_local size_t smem_set = 0;
-    if (smem + 1024 > 48 * 1024 && smem > smem_set) {        // (+ the kernel's small static arrays)
-        cudaError_t e = cudaFuncSetAttribute(epi_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto ensure = [&](size_t smem) -> cudaError_t {
+        if (smem + 1024 > 48 * 1024 && smem > smem_set) {        // (+ the kernel's small static arrays)
+            cudaError_t e = cudaFuncSetAttribute(epi_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            smem_set = smem;
+        }
+        return cudaSuccess;
+    };
+    // Shared memory is a per-launch size: above 64 KB the order blocks' pixel list would cut the residency of every transposition
+    // block of the same launch, so maps that large order their pixels in a launch of their own (a no-op on a cached camera pair).
+    if (s.do_order && smem_order > 64 * 1024) {
+        StageArgs o = s;
+        o.do_ref = 0; o.do_src = 0; o.Wf = nullptr; o.w_planes = nullptr;
+        cudaError_t e = ensure(smem_order);
         if (e != cudaSuccess) return e;
-        smem_set = smem;
+        e = launch_pdl(epi_stage_kernel, dim3((unsigned)N), dim3(stg::NT), smem_order, st, o);
+        if (e != cudaSuccess) return e;
+        s.do_order = 0; s.zero_words = nullptr;                  // the order launch has zeroed the counters
     }
+    const int grid = (s.do_order ? N : 0) + 2 * tiles + wblocks;
+    const size_t smem = (s.do_order && smem_order > smem_tile) ? smem_order : smem_tile;
+    cudaError_t e = ensure(smem);
+    if (e != cudaSuccess) return e;
     return launch_pdl(epi_stage_kernel, dim3((unsigned)grid), dim3(stg::NT), smem, st, s);
 }
 

@@ -374,13 +374,12 @@ def test_host_streamer_matches_direct_call():
         assert torch.equal(o, out.cpu()) and torch.equal(a_, attn.cpu()) and torch.equal(c, corr.cpu())
 
 
-PIPE_MAX_HW = 16384
 SWEEP = [  # (N, C, H, W, K)   BASELINE config 5 corners + map sizes on both sides of the tensor-core kernel's limits
     (1, 64, 64, 64, 16), (1, 128, 64, 64, 32), (1, 256, 64, 64, 128), (1, 512, 32, 32, 64),   # C=512: two query-panel halves
     (2, 512, 64, 64, 128), (1, 384, 48, 40, 32), (1, 264, 40, 40, 16),                         # wide corners, C % 64 != 0 above 256
     (1, 64, 128, 128, 32),                                                                       # H*W = 16384: largest tile-kernel map
     (1, 32, 160, 96, 16),                                                                        # non-square
-    (1, 16, 144, 144, 16),                                                                       # H*W > 16384 -> warp kernel
+    (1, 16, 144, 144, 16), (2, 24, 100, 400, 64), (1, 8, 300, 100, 16),                          # H*W > 16384: row-windowed union; H > 256 -> warp kernel
     (2, 40, 24, 40, 48),                                                                         # C % 32 != 0, partial tiles
     (1, 64, 256, 256, 16),                                                                       # literal 256x256 feature-map reading
 ]
@@ -397,7 +396,8 @@ def test_sweep_shapes_vs_oracle(shape):
     f1 = syn.features(N, C, H, W, "randn", 5); f2 = syn.features(N, C, H, W, "randn", 6)
     # the documented limits of the pipelined tensor-core kernel: inside them the kernel is FORCED, so a shape
     # that silently fell back to another kernel would fail with EINVAL instead of passing
-    pipe_ok = C % 8 == 0 and 8 <= C <= 512 and H * W <= PIPE_MAX_HW and K <= 128 and min(4 * K, 4 * max(H, W)) <= 256
+    map_ok = H * W <= 16384 or (H <= 256 and W <= 1024 and H * W <= 65536)            # above 16384 pixels: row-windowed union bitmap
+    pipe_ok = C % 8 == 0 and 8 <= C <= 512 and map_ok and K <= 128 and min(4 * K, 4 * max(H, W)) <= 256
     out, corr, attn, locs = epi.epipolar_fusion(dev(f1), dev(f2), dev(P1), dev(P2), K=K, correct_normalize=True, want_locs=True,
                                                 variant="pipe" if pipe_ok else "auto")
     torch.cuda.synchronize()
