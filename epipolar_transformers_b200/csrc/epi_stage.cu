@@ -65,6 +65,7 @@ struct StageArgs {
     __nv_bfloat16 *w_planes;
     int N, C, H, W;
     int do_ref, do_src, do_order;
+    int persist;                      // > 0: whole vectorisable tiles only -> `persist` streaming blocks loop over the tiles
     GeomCfg gc;
 };
 
@@ -278,9 +279,12 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
     const int tiles_p = (HW + TPX - 1) / TPX, tiles_c = (C + TC - 1) / TC;
     const int per_map = tiles_p * tiles_c * s.N;
     int lin = (int)blockIdx.x - nord;
-    if (lin >= 2 * per_map) {
+    const int wblocks = (s.Wf && s.w_planes) ? (C * C / 8 + NT - 1) / NT : 0;
+    // block roles after the order blocks: [tiles | weight blocks], or with streaming blocks [weight blocks | streaming blocks]
+    const int wlin = s.persist ? lin : lin - 2 * per_map;
+    if (wlin >= 0 && wlin < wblocks) {
         // folded z weight [C out][C in] fp32 -> bf16 (hi, lo) planes (B operand of the z GEMM), 8 elements per thread
-        const size_t e0 = ((size_t)(lin - 2 * per_map) * NT + t) * 8, tot = (size_t)C * C;
+        const size_t e0 = ((size_t)wlin * NT + t) * 8, tot = (size_t)C * C;
         if (e0 < tot) {
             const float4 a4 = __ldg(reinterpret_cast<const float4 *>(s.Wf + e0)), b4 = __ldg(reinterpret_cast<const float4 *>(s.Wf + e0 + 4));
             float f[8] = {a4.x, a4.y, a4.z, a4.w, b4.x, b4.y, b4.z, b4.w};
@@ -302,6 +306,91 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
         }
         return;
     }
+    constexpr int QW = TPX / 4, RPP = NT / QW, RPASS = TC / RPP;        // float4 per channel row, channel rows per pass, passes
+    // ---- whole NCHW tiles ----
+    // Fast path (whole NCHW tile): the (hi, lo) split happens BEFORE the transposition, on bf16x2 words of two adjacent channels,
+    // so shared memory carries 2 x 8 KB of 32-bit words instead of 16 KB of fp32 scalars.  Half-warps load 256-byte rows of two
+    // adjacent channels and swap halves (lanes < 16 keep pixels 4q, 4q+1; lanes >= 16 pixels 4q+2, 4q+3).  Word (px, cpair) lives at
+    // row px, position ((g ^ a) << 2) | (k ^ b) with g = cpair / 4, k = cpair % 4, (a, b) = bits of px / 2: the 32 lanes of a
+    // store (one channel pair, 32 pixels of one parity) hit 32 different banks, and the 16-byte reads of a pixel's 8 channel groups
+    // cover its whole 128-byte row; the reader undoes the k ^ b order with four selects.
+    uint32_t *whi = reinterpret_cast<uint32_t *>(dyn), *wlo = whi + TPX * 32;
+    const int fq = t & 15, hsel = (t >> 4) & 1, fw = t >> 5;
+    auto fast_load = [&](const float *spn, int64_t scn, int c0n, int p0n, float4 *v) {
+#pragma unroll
+        for (int i = 0; i < RPASS; i++) v[i] = __ldg(reinterpret_cast<const float4 *>(spn + (int64_t)(c0n + 2 * fw + hsel + i * RPP) * scn + p0n + fq * 4));
+    };
+    auto fast_split = [&](const float4 *v) {            // registers -> (hi, lo) words in shared memory
+#pragma unroll
+        for (int i = 0; i < RPASS; i++) {
+            const float sx = hsel ? v[i].x : v[i].z, sy = hsel ? v[i].y : v[i].w;          // what the partner lane needs
+            const float rx = __shfl_xor_sync(0xffffffffu, sx, 16), ry = __shfl_xor_sync(0xffffffffu, sy, 16);
+            // pixel pair of this lane: even channel first
+            const float e0 = hsel ? rx : v[i].x, o0 = hsel ? v[i].z : rx;                   // pixel 4q + 2 hsel
+            const float e1 = hsel ? ry : v[i].y, o1 = hsel ? v[i].w : ry;                   // pixel 4q + 2 hsel + 1
+            const int cpair = fw + 8 * i, g = cpair >> 2, k = cpair & 3;
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const float fe = u ? e1 : e0, fo = u ? o1 : o0;
+                const __nv_bfloat162 hv = __floats2bfloat162_rn(fe, fo);
+                const float2 hf = __bfloat1622float2(hv);
+                const __nv_bfloat162 lv = __floats2bfloat162_rn(fe - hf.x, fo - hf.y);
+                const int px = 4 * fq + 2 * hsel + u, sw5 = (px >> 1) & 31;
+                const int pos = px * 32 + (((g ^ (sw5 >> 2)) << 2) | (k ^ (sw5 & 3)));
+                whi[pos] = *reinterpret_cast<const uint32_t *>(&hv);
+                wlo[pos] = *reinterpret_cast<const uint32_t *>(&lv);
+            }
+        }
+    };
+    auto fast_store = [&](__nv_bfloat16 *hin, __nv_bfloat16 *lon, int nn, int c0n, int p0n) {     // shared memory -> pixel-major planes
+        const int g = t & 7, pl = t >> 3;
+#pragma unroll
+        for (int i = 0; i < TPX / (NT / 8); i++) {
+            const int px = pl + i * (NT / 8), sw5 = (px >> 1) & 31;
+            const int pos = px * 32 + ((g ^ (sw5 >> 2)) << 2);
+            uint4 h4 = *reinterpret_cast<const uint4 *>(whi + pos), l4 = *reinterpret_cast<const uint4 *>(wlo + pos);
+            if (sw5 & 1) { uint32_t x_; x_ = h4.x; h4.x = h4.y; h4.y = x_; x_ = h4.z; h4.z = h4.w; h4.w = x_; x_ = l4.x; l4.x = l4.y; l4.y = x_; x_ = l4.z; l4.z = l4.w; l4.w = x_; }
+            if (sw5 & 2) { uint32_t x_; x_ = h4.x; h4.x = h4.z; h4.z = x_; x_ = h4.y; h4.y = h4.w; h4.w = x_; x_ = l4.x; l4.x = l4.z; l4.z = x_; x_ = l4.y; l4.y = l4.w; l4.w = x_; }
+            const size_t o = ((size_t)nn * HW + p0n + px) * C + c0n + g * 8;
+            *reinterpret_cast<uint4 *>(hin + o) = h4;
+            *reinterpret_cast<uint4 *>(lon + o) = l4;
+        }
+    };
+    const size_t plane_elems_all = (size_t)s.N * HW * C;
+    if (s.persist) {
+        // Streaming blocks: every tile is a whole, vectorisable NCHW tile (host check).  A block walks tiles lin, lin + stride, ...
+        // and issues the loads of its NEXT tile before it stores the current one, so HBM reads stay in flight for the whole launch
+        // (one tile per block left the memory system idle while each block converted and stored).
+        const int nt = 2 * per_map, stride = s.persist;
+        int cur = lin - wblocks;
+        if (cur >= nt) return;
+        auto decode = [&](int l, int &mp, int &nn, int &c0n, int &p0n) {
+            mp = l & 1; l >>= 1;                         // reference and source tiles alternate (see below)
+            nn = l / (tiles_p * tiles_c);
+            const int rem = l - nn * (tiles_p * tiles_c);
+            const int ct = rem / tiles_p;
+            c0n = ct * TC; p0n = (rem - ct * tiles_p) * TPX;
+        };
+        float4 v[RPASS];
+        int mp, nn, c0n, p0n;
+        decode(cur, mp, nn, c0n, p0n);
+        fast_load((mp ? s.src : s.ref) + (int64_t)nn * (mp ? s.src_stride[0] : s.ref_stride[0]), mp ? s.src_stride[1] : s.ref_stride[1], c0n, p0n, v);
+        while (true) {
+            fast_split(v);
+            __syncthreads();
+            const int nxt = cur + stride;
+            int mp2 = 0, nn2 = 0, c02 = 0, p02 = 0;
+            if (nxt < nt) {
+                decode(nxt, mp2, nn2, c02, p02);
+                fast_load((mp2 ? s.src : s.ref) + (int64_t)nn2 * (mp2 ? s.src_stride[0] : s.ref_stride[0]), mp2 ? s.src_stride[1] : s.ref_stride[1], c02, p02, v);
+            }
+            __nv_bfloat16 *hin = s.planes + (size_t)(2 * mp) * plane_elems_all;
+            fast_store(hin, hin + plane_elems_all, nn, c0n, p0n);
+            if (nxt >= nt) return;
+            __syncthreads();
+            cur = nxt; mp = mp2; nn = nn2; c0n = c02; p0n = p02;
+        }
+    }
     // reference and source tiles alternate in block order: when the source map is a peer-mapped tensor of another GPU its
     // NVLink reads (~0.77 TB/s, microsecond latency) overlap the local reference tiles instead of queueing behind them
     int map = 0;
@@ -316,7 +405,14 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
     const size_t plane_elems = (size_t)s.N * HW * C;
     __nv_bfloat16 *hi = s.planes + (size_t)(2 * map) * plane_elems, *lo = hi + plane_elems;
     const bool vec = (sw == 1) && (sh == W) && (HW % 4 == 0) && (sc % 4 == 0) && ((reinterpret_cast<uintptr_t>(sp) & 15) == 0);
-    constexpr int QW = TPX / 4, RPP = NT / QW, RPASS = TC / RPP;        // float4 per channel row, channel rows per pass, passes
+    if (vec && sc != 1 && p0 + TPX <= HW && c0 + TC <= C) {
+        float4 v[RPASS];
+        fast_load(sp, sc, c0, p0, v);
+        fast_split(v);
+        __syncthreads();
+        fast_store(hi, lo, n, c0, p0);
+        return;
+    }
     if (sc != 1) {
         const int q = t % QW, cy = t / QW;
         float4 v[RPASS];
@@ -380,7 +476,7 @@ cudaError_t launch_stage(const float *ref, const int64_t ref_stride[4], const fl
     for (int i = 0; i < 4; i++) { s.ref_stride[i] = ref_stride[i]; s.src_stride[i] = src_stride[i]; }
     s.planes = planes; s.P_ref = P_ref; s.P_src = P_src; s.pair_geom = pair_geom; s.order = order; s.order_key = order_key; s.Wf = Wf; s.w_planes = w_planes; s.w_add_identity = w_add_identity;
     s.zero_words = zero_words; s.N = N; s.C = C; s.H = H; s.W = W; s.gc = gc;
-    s.do_ref = 1; s.do_src = 1; s.do_order = (P_ref && P_src && order) ? 1 : 0;
+    s.do_ref = 1; s.do_src = 1; s.do_order = (P_ref && P_src && order) ? 1 : 0; s.persist = 0;
     const int tiles = ((H * W + stg::TPX - 1) / stg::TPX) * ((C + stg::TC - 1) / stg::TC) * N;
     const int wblocks = (Wf && w_planes) ? (C * C / 8 + stg::NT - 1) / stg::NT : 0;        // C % 8 == 0
     // dynamic shared memory: the transposition tile, or (order blocks) 16 KB histogram + 2 B per pixel
@@ -399,14 +495,29 @@ cudaError_t launch_stage(const float *ref, const int64_t ref_stride[4], const fl
     // block of the same launch, so maps that large order their pixels in a launch of their own (a no-op on a cached camera pair).
     if (s.do_order && smem_order > 64 * 1024) {
         StageArgs o = s;
-        o.do_ref = 0; o.do_src = 0; o.Wf = nullptr; o.w_planes = nullptr;
+        o.do_ref = 0; o.do_src = 0; o.Wf = nullptr; o.w_planes = nullptr; o.persist = 0;
         cudaError_t e = ensure(smem_order);
         if (e != cudaSuccess) return e;
         e = launch_pdl(epi_stage_kernel, dim3((unsigned)N), dim3(stg::NT), smem_order, st, o);
         if (e != cudaSuccess) return e;
         s.do_order = 0; s.zero_words = nullptr;                  // the order launch has zeroed the counters
     }
-    const int grid = (s.do_order ? N : 0) + 2 * tiles + wblocks;
+    // streaming blocks when every tile of both maps is a whole, 16-byte-vectorisable NCHW tile
+    auto whole = [&](const float *b, const int64_t *sd) {
+        return sd[3] == 1 && sd[2] == W && sd[1] % 4 == 0 && sd[0] % 4 == 0 && sd[1] != 1 && (reinterpret_cast<uintptr_t>(b) & 15) == 0;
+    };
+    static thread_local int sms_cached = 0;
+    if (!sms_cached) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&sms_cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms_cached <= 0) sms_cached = 148;
+    }
+    s.persist = 0;
+    if ((H * W) % stg::TPX == 0 && C % stg::TC == 0 && whole(ref, ref_stride) && whole(src, src_stride)) {
+        const int slots = 5 * sms_cached;                      // 5 resident blocks per SM (__launch_bounds__)
+        s.persist = 2 * tiles < slots ? 2 * tiles : slots;
+    }
+    const int grid = (s.do_order ? N : 0) + wblocks + (s.persist ? s.persist : 2 * tiles);
     const size_t smem = (s.do_order && smem_order > smem_tile) ? smem_order : smem_tile;
     cudaError_t e = ensure(smem);
     if (e != cudaSuccess) return e;

@@ -4,7 +4,8 @@
 // restates  finalout = bn(z(out)) [+ out]   /root/reference/modeling/layers/epipolar.py:249-253 (eval-mode BN folded
 // into Wf, bf by epi_fold_z_bn_f32) and  ret + feat   /root/reference/modeling/backbones/resnet.py:388.
 //
-// One CTA per 128 pixels and block of up to 256 output channels (blockIdx.y; two blocks when 256 < C <= 512):
+// One CTA per 128 pixels and block of 128 output channels (blockIdx.y); small CTAs (69 KB, one K panel in flight) so that three
+// are resident per SM and their load / MMA / store phases overlap each other:
 // D[128 px, C out] = X[128 px, C]·Wfᵀ with X supplied by the fusion kernel as bf16
 // (hi, lo) planes [N·HW, C] (K-major rows) and Wf split to (hi, lo) while it is staged.  Three MMAs per
 // product (hi·hi + hi·lo + lo·hi), fp32 accumulation in TMEM (M=128, N=C<=256), K streamed in 64-channel
@@ -23,11 +24,15 @@ namespace epi {
 using namespace umma;
 
 namespace zg {
-constexpr int NT = 512;
+constexpr int NT = 256;
 constexpr uint32_t A_PLANE = 16384;                 // 128 rows x 128 B
-constexpr uint32_t B_PLANE = 32768;                 // 256 rows x 128 B
-constexpr uint32_t STAGE = 2 * A_PLANE + 2 * B_PLANE;   // 96 KB
-constexpr uint32_t SMEM_ALLOC = 2 * STAGE + 1024 + 128;
+constexpr int NB = 128;                             // output channels per CTA (MMA N)
+constexpr uint32_t B_PLANE = 16384;                 // 128 rows x 128 B
+constexpr uint32_t STAGE = 2 * A_PLANE + 2 * B_PLANE;   // 64 KB: one K panel of (A hi, A lo, W hi, W lo)
+constexpr int OT = 132;                             // epilogue tile pitch (floats)
+constexpr uint32_t TILE_BYTES = NB * OT * 4;        // 67 584 B: the epilogue tile re-uses the stage
+constexpr uint32_t BUF_BYTES = TILE_BYTES > STAGE ? TILE_BYTES : STAGE;
+constexpr uint32_t SMEM_ALLOC = BUF_BYTES + 1024 + 128;     // ~69 KB: three CTAs per SM overlap each other's load / MMA / store phases
 
 // 2-D tiled TMA load of a [128 rows x 64 bf16] box into a swizzled panel, completion counted on `bar`
 __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
@@ -38,27 +43,48 @@ __device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *t
 }
 }  // namespace zg
 
-__global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z, const __grid_constant__ CUtensorMap tm_hi,
+__global__ void __launch_bounds__(zg::NT, 2) epi_zgemm_kernel(const ZGemmArgs z, const __grid_constant__ CUtensorMap tm_hi,
                                                               const __grid_constant__ CUtensorMap tm_lo,
                                                               const __grid_constant__ CUtensorMap tw_hi,
                                                               const __grid_constant__ CUtensorMap tw_lo) {
     using namespace zg;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * STAGE);       // [0,1] stage landed (TMA), [2,3] MMAs done with stage, [4] all MMAs done
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * STAGE + 64);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + BUF_BYTES);       // [0] panel landed (TMA), [1] MMAs done with the panel, [2] all MMAs done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + BUF_BYTES + 64);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = z.C, HW = z.HW, W = z.W;
     const int tiles = (HW + 127) / 128;
     const int n = blockIdx.x / tiles, p0 = (blockIdx.x % tiles) * 128;
     const int nq = (C + 63) / 64;                      // K panels of 64 channels
-    const int oc0 = (int)blockIdx.y * 256;            // this CTA's block of output channels
-    const int CO = min(256, C - oc0);
-    const __nv_bfloat16 *xh = z.x_hi + (size_t)n * HW * C, *xl = z.x_lo + (size_t)n * HW * C;
+    const int oc0 = (int)blockIdx.y * NB;             // this CTA's block of output channels
+    const int CO = min(NB, C - oc0);
 
     pdl_launch_dependents();
-    if (warp == 0) tmem_alloc(tmem_slot, 256);
-    if (tid == 32) { for (int i = 0; i < 5; i++) mbar_init(&bars[i], 1); mbar_fence_init(); }
+    // The bias and the caller's residual (inputs of the whole forward, not products of the previous launches) are fetched into
+    // registers FIRST: their latency is paid under the previous kernel's tail and this kernel's main loop instead of once per
+    // output row of the epilogue (16 dependent round trips per warp — 30 % of the kernel's stall samples before the hoist).
+    const bool addr = z.ref && z.add_ref;
+    const bool vec = (z.y_stride[3] == 1) && (z.y_stride[2] == W) && (HW % 4 == 0) && (z.y_stride[1] % 4 == 0) && (z.y_stride[0] % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(z.y) & 15) == 0) &&
+                     (!addr || ((z.ref_stride[3] == 1) && (z.ref_stride[2] == W) && (z.ref_stride[1] % 4 == 0) && (z.ref_stride[0] % 4 == 0) &&
+                                ((reinterpret_cast<uintptr_t>(z.ref) & 15) == 0)));
+    constexpr int ROWS = NB / (NT / 32);              // output rows per warp
+    float4 res[ROWS];
+    float bias[ROWS];
+    {
+        const int p = p0 + lane * 4;
+#pragma unroll
+        for (int k = 0; k < ROWS; k++) {
+            const int ol = warp + k * (NT / 32);
+            res[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            bias[k] = ol < CO ? __ldg(z.bf + oc0 + ol) : 0.f;      // folded bias: written long before the staging launch
+            if (addr && vec && p + 3 < HW && ol < CO)
+                res[k] = __ldg(reinterpret_cast<const float4 *>(z.ref + (int64_t)n * z.ref_stride[0] + (int64_t)(oc0 + ol) * z.ref_stride[1] + p));
+        }
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, NB);
+    if (tid == 32) { for (int i = 0; i < 3; i++) mbar_init(&bars[i], 1); mbar_fence_init(); }
     if (tid == 64) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
@@ -71,25 +97,21 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
     const uint32_t tmem = *tmem_slot;
     pdl_wait();                                        // the fused kernel's feature planes
 
-    // One thread drives the whole main loop: TMA loads of the (A, W) panels into a 2-stage ring, tcgen05.mma issue, commits.
-    // A: 128 pixel rows x 64 channels of the (hi, lo) planes of x;  B: C output rows x 64 input channels of the (hi, lo) planes of Wf.
+    // One thread drives the main loop: TMA load of a K panel (A: 128 pixel rows x 64 channels of the (hi, lo) planes of x; B: NB output
+    // rows x 64 input channels of the (hi, lo) planes of Wf), three MMAs per 16-channel step, commit, next panel.
     if (tid == 0) {
-        auto load = [&](int q) {
-            uint8_t *st = smem + (q & 1) * STAGE;
-            mbar_arrive_expect_tx(&bars[q & 1], 2 * A_PLANE + 2 * (uint32_t)(C < 256 ? C : 256) * 128u);   // W box = min(C, 256) rows x 128 B
-            tma_load_2d(st, &tm_hi, q * 64, n * HW + p0, &bars[q & 1]);
-            tma_load_2d(st + A_PLANE, &tm_lo, q * 64, n * HW + p0, &bars[q & 1]);
-            tma_load_2d(st + 2 * A_PLANE, &tw_hi, q * 64, oc0, &bars[q & 1]);
-            tma_load_2d(st + 2 * A_PLANE + B_PLANE, &tw_lo, q * 64, oc0, &bars[q & 1]);
-        };
-        load(0);
-        if (nq > 1) load(1);
+        const uint32_t wrows = (uint32_t)(C < NB ? C : NB);            // W box rows (the tensor map's box)
         const uint32_t idesc = make_idesc_bf16(128, (uint32_t)((CO + 15) & ~15), 0, 0);
         for (int q = 0; q < nq; q++) {
-            const uint32_t buf = q & 1;
-            for (uint32_t it = 0; !mbar_try_wait(&bars[buf], (q >> 1) & 1); ++it) if (it > (1u << 24)) __trap();
+            if (q > 0) for (uint32_t it = 0; !mbar_try_wait(&bars[1], (q - 1) & 1); ++it) if (it > (1u << 24)) __trap();
+            mbar_arrive_expect_tx(&bars[0], 2 * A_PLANE + 2 * wrows * 128u);
+            tma_load_2d(smem, &tm_hi, q * 64, n * HW + p0, &bars[0]);
+            tma_load_2d(smem + A_PLANE, &tm_lo, q * 64, n * HW + p0, &bars[0]);
+            tma_load_2d(smem + 2 * A_PLANE, &tw_hi, q * 64, oc0, &bars[0]);
+            tma_load_2d(smem + 2 * A_PLANE + B_PLANE, &tw_lo, q * 64, oc0, &bars[0]);
+            for (uint32_t it = 0; !mbar_try_wait(&bars[0], q & 1); ++it) if (it > (1u << 24)) __trap();
             tc_fence_after();
-            const uint32_t sa = smem_u32(smem + buf * STAGE), sb = sa + 2 * A_PLANE;
+            const uint32_t sa = smem_u32(smem), sb = sa + 2 * A_PLANE;
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
                 const uint64_t a_hi = make_smem_desc(sa + ks * 32, 16, 1024), a_lo = make_smem_desc(sa + A_PLANE + ks * 32, 16, 1024);
@@ -98,27 +120,22 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
                 mma_bf16(tmem, a_hi, b_lo, idesc, 1u);
                 mma_bf16(tmem, a_lo, b_hi, idesc, 1u);
             }
-            mma_commit(&bars[2 + buf]);
-            if (q + 2 < nq) {
-                for (uint32_t it = 0; !mbar_try_wait(&bars[2 + buf], (q >> 1) & 1); ++it) if (it > (1u << 24)) __trap();
-                load(q + 2);
-            }
+            mma_commit(&bars[1]);
         }
-        mma_commit(&bars[4]);
+        mma_commit(&bars[2]);
     }
-    for (uint32_t it = 0; !mbar_try_wait(&bars[4], 0); ++it) if (it > (1u << 24)) __trap();
+    for (uint32_t it = 0; !mbar_try_wait(&bars[2], 0); ++it) if (it > (1u << 24)) __trap();
     tc_fence_after();
 
     // ---- epilogue ------------------------------------------------------------------------------------------------
-    // phase 1 (thread <-> pixel = TMEM lane, 16 warps = 4 lane quadrants x 4 channel groups): accumulator -> shared tile
+    // phase 1 (thread <-> pixel = TMEM lane, 8 warps = 4 lane quadrants x 2 channel groups): accumulator -> shared tile
     //   [channel][128 pixels] (the operand stages are free now).  The ZRESIDUAL needs no pass: the staged weight is Wf + I;
     // phase 2 (warp <-> channel row, lane <-> 4 consecutive pixels): + bias + caller residual, 512-byte row segments of the NCHW output
     //   per warp instruction.  Falls back to per-element addressing for strides that are not pixel-contiguous.
-    float *otile = reinterpret_cast<float *>(smem);            // [C][132] fp32 <= 256 * 132 * 4 = 135168 B of the 196608 B stage area
-    constexpr int OT = 132;
+    float *otile = reinterpret_cast<float *>(smem);            // [NB][132] fp32 over the (now idle) stage
     {
         const int r = (warp & 3) * 32 + lane;
-        for (int cb = (warp >> 2) * 32; cb < CO; cb += 128) {
+        for (int cb = (warp >> 2) * 32; cb < CO; cb += (NT / 128) * 32) {
             float v[32];
             tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + cb, v);
             tmem_ld_wait();
@@ -130,23 +147,18 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
     tc_fence_before();
     __syncthreads();
     {
-        const bool addr = z.ref && z.add_ref;
-        const bool vec = (z.y_stride[3] == 1) && (z.y_stride[2] == W) && (HW % 4 == 0) && (z.y_stride[1] % 4 == 0) && (z.y_stride[0] % 4 == 0) &&
-                         ((reinterpret_cast<uintptr_t>(z.y) & 15) == 0) &&
-                         (!addr || ((z.ref_stride[3] == 1) && (z.ref_stride[2] == W) && (z.ref_stride[1] % 4 == 0) && (z.ref_stride[0] % 4 == 0) &&
-                                    ((reinterpret_cast<uintptr_t>(z.ref) & 15) == 0)));
         const int pp = lane * 4, p = p0 + pp;
-        for (int ol = warp; ol < CO; ol += NT / 32) {
+#pragma unroll
+        for (int k = 0; k < ROWS; k++) {
+            const int ol = warp + k * (NT / 32);
+            if (ol >= CO) break;
             const int o = oc0 + ol;
             const float4 t = *reinterpret_cast<const float4 *>(otile + ol * OT + pp);
-            const float b = __ldg(z.bf + o);
+            const float b = bias[k];
             float y[4] = {t.x + b, t.y + b, t.z + b, t.w + b};
             if (vec && p + 3 < HW) {
-                if (addr) {
-                    const float4 r4 = __ldg(reinterpret_cast<const float4 *>(z.ref + (int64_t)n * z.ref_stride[0] + (int64_t)o * z.ref_stride[1] + p));
-                    y[0] += r4.x; y[1] += r4.y; y[2] += r4.z; y[3] += r4.w;
-                }
-                *reinterpret_cast<float4 *>(z.y + (int64_t)n * z.y_stride[0] + (int64_t)o * z.y_stride[1] + p) = make_float4(y[0], y[1], y[2], y[3]);
+                *reinterpret_cast<float4 *>(z.y + (int64_t)n * z.y_stride[0] + (int64_t)o * z.y_stride[1] + p) =
+                    make_float4(y[0] + res[k].x, y[1] + res[k].y, y[2] + res[k].z, y[3] + res[k].w);
             } else {
                 for (int e = 0; e < 4 && p + e < HW; e++) {
                     const int py = (p + e) / W, px = (p + e) % W;
@@ -159,10 +171,233 @@ __global__ void __launch_bounds__(zg::NT, 1) epi_zgemm_kernel(const ZGemmArgs z,
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(tmem, NB);
 }
 
-bool zgemm_supported(int C) { return C % 64 == 0 && C >= 64 && C <= 512; }   // whole 64-channel TMA panels; two output blocks above 256
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent variant (C <= 256, the shapes of the reference's configs): one CTA per SM keeps its block of the weight (128 output
+// channels x C, hi and lo: up to 128 KB) RESIDENT in shared memory and walks pixel tiles; the A panels stream through a 2-stage TMA
+// ring, the accumulator is double-buffered in TMEM, and the roles are separate warps (warp 0: TMA producer, warp 1: MMA issuer,
+// warps 2-9: epilogue), so the loads of tile k+1 and its MMAs run under the epilogue of tile k.  The one-tile-per-CTA kernel above
+// spent two thirds of its time in load -> MMA -> store latency chains that nothing overlapped.
+// ---------------------------------------------------------------------------------------------------------------------
+#ifdef EPI_PIPE_TIMERS
+__device__ long long g_zg_trace[64];
+__device__ unsigned long long g_zg_span[4];      // min start, max start, min end, max end (globaltimer ns)
+#define ZTR(i) do { if (blockIdx.x == 0) g_zg_trace[i] = clock64(); } while (0)
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#else
+#define ZTR(i) do { } while (0)
+#endif
+namespace zp {
+constexpr int NT = 320;
+constexpr int NB = 128;
+constexpr int HB = 64;                              // output channels per epilogue pass (half tile)
+constexpr int OT = 132;
+constexpr uint32_t A_PLANE = 16384, A_STAGE = 2 * A_PLANE;
+constexpr uint32_t W_PLANE = 16384, W_PANEL = 2 * W_PLANE;      // [hi 128 rows x 128 B | lo]
+constexpr uint32_t OFF_W = 0;                       // 4 K panels
+constexpr uint32_t OFF_A = 4 * W_PANEL;             // 2 stages
+constexpr uint32_t OFF_T = OFF_A + 2 * A_STAGE;     // [HB][132] fp32
+constexpr uint32_t OFF_BAR = OFF_T + HB * OT * 4;
+constexpr uint32_t SMEM_ALLOC = OFF_BAR + 256 + 1024;
+static_assert(SMEM_ALLOC <= 232448, "fits the opt-in shared memory");
+__device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
+    for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) if (it > (1u << 24)) __trap();
+}
+}  // namespace zp
+
+__global__ void __launch_bounds__(zp::NT, 1) epi_zgemm_persist_kernel(const ZGemmArgs z, const __grid_constant__ CUtensorMap tm_hi,
+                                                                      const __grid_constant__ CUtensorMap tm_lo,
+                                                                      const __grid_constant__ CUtensorMap tw_hi,
+                                                                      const __grid_constant__ CUtensorMap tw_lo) {
+    using namespace zp;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);     // [0] W landed, [1,2] A stage full, [3,4] A stage free, [5,6] accumulator full, [7,8] accumulator free
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = z.C, HW = z.HW, W = z.W;
+    const int tiles = (HW + 127) / 128, PT = z.N * tiles;
+    const int nq = (C + 63) / 64;
+    const int nblk = (C + NB - 1) / NB;
+    const int nb = (int)blockIdx.x % nblk, first = (int)blockIdx.x / nblk, step = (int)gridDim.x / nblk;   // gridDim.x % nblk == 0
+    const int oc0 = nb * NB, CO = min(NB, C - oc0);
+#ifdef EPI_PIPE_TIMERS
+    if (tid == 0) { const unsigned long long g = gtime(); atomicMin(&g_zg_span[0], g); atomicMax(&g_zg_span[1], g); }
+    if (tid == 0) ZTR(0);
+#endif
+
+    pdl_launch_dependents();
+    // per-thread constants of the epilogue: this warp's rows of both half tiles
+    const int ew = warp - 2;                          // epilogue warp 0..7
+    float bias[2][HB / 8];
+    if (ew >= 0) {
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int k = 0; k < HB / 8; k++) {
+                const int ol = h * HB + ew + 8 * k;
+                bias[h][k] = ol < CO ? __ldg(z.bf + oc0 + ol) : 0.f;    // folded bias: written before the staging launch was issued
+            }
+    }
+    if (warp == 2) tmem_alloc(tmem_slot, 256);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        for (int i = 0; i < 2; i++) { mbar_init(&bars[1 + i], 1); mbar_init(&bars[3 + i], 1); mbar_init(&bars[5 + i], 1); mbar_init(&bars[7 + i], 1); }
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tw_hi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tw_lo) : "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (tid == 0) ZTR(1);
+    pdl_wait();                                        // the fused kernel's feature planes (and, transitively, the staged weight)
+    if (tid == 0) ZTR(2);
+
+    if (warp == 0) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0 && first < PT) {
+            const uint32_t wrows = (uint32_t)(C < NB ? C : NB);
+            mbar_arrive_expect_tx(&bars[0], (uint32_t)nq * 2u * wrows * 128u);
+            for (int q = 0; q < nq; q++) {
+                zg::tma_load_2d(smem + OFF_W + q * W_PANEL, &tw_hi, q * 64, oc0, &bars[0]);
+                zg::tma_load_2d(smem + OFF_W + q * W_PANEL + W_PLANE, &tw_lo, q * 64, oc0, &bars[0]);
+            }
+            uint32_t ac = 0;
+            for (int pt = first; pt < PT; pt += step) {
+                const int n = pt / tiles, p0 = (pt % tiles) * 128;
+                for (int q = 0; q < nq; q++, ac++) {
+                    const uint32_t s = ac & 1u;
+                    if (ac >= 2) wait_bar(&bars[3 + s], ((ac >> 1) - 1u) & 1u);
+                    mbar_arrive_expect_tx(&bars[1 + s], 2 * A_PLANE);
+                    zg::tma_load_2d(smem + OFF_A + s * A_STAGE, &tm_hi, q * 64, n * HW + p0, &bars[1 + s]);
+                    zg::tma_load_2d(smem + OFF_A + s * A_STAGE + A_PLANE, &tm_lo, q * 64, n * HW + p0, &bars[1 + s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ---------------- MMA issuer ----------------
+        if (lane == 0 && first < PT) {
+            const uint32_t idesc = make_idesc_bf16(128, (uint32_t)((CO + 15) & ~15), 0, 0);
+            wait_bar(&bars[0], 0);
+            ZTR(3);
+            uint32_t ac = 0;
+            int k = 0;
+            for (int pt = first; pt < PT; pt += step, k++) {
+                const uint32_t buf = (uint32_t)k & 1u;
+                if (k >= 2) wait_bar(&bars[7 + buf], (uint32_t)((k >> 1) - 1) & 1u);
+                tc_fence_after();
+                for (int q = 0; q < nq; q++, ac++) {
+                    const uint32_t s = ac & 1u;
+                    wait_bar(&bars[1 + s], (ac >> 1) & 1u);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + OFF_A + s * A_STAGE), sb = smem_u32(smem + OFF_W + q * W_PANEL);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        const uint64_t a_hi = make_smem_desc(sa + ks * 32, 16, 1024), a_lo = make_smem_desc(sa + A_PLANE + ks * 32, 16, 1024);
+                        const uint64_t b_hi = make_smem_desc(sb + ks * 32, 16, 1024), b_lo = make_smem_desc(sb + W_PLANE + ks * 32, 16, 1024);
+                        mma_bf16(tmem + buf * NB, a_hi, b_hi, idesc, (q | ks) ? 1u : 0u);
+                        mma_bf16(tmem + buf * NB, a_hi, b_lo, idesc, 1u);
+                        mma_bf16(tmem + buf * NB, a_lo, b_hi, idesc, 1u);
+                    }
+                    mma_commit(&bars[3 + s]);
+                }
+                mma_commit(&bars[5 + buf]);
+                if (k < 8) ZTR(8 + k);
+            }
+        }
+    } else {
+        // ---------------- epilogue (8 warps): TMEM -> [64 channels][128 pixels] tile -> + bias (+ residual) -> NCHW ----------------
+        float *otile = reinterpret_cast<float *>(smem + OFF_T);
+        const bool addr = z.ref && z.add_ref;
+        const bool vec = (z.y_stride[3] == 1) && (z.y_stride[2] == W) && (HW % 4 == 0) && (z.y_stride[1] % 4 == 0) && (z.y_stride[0] % 4 == 0) &&
+                         ((reinterpret_cast<uintptr_t>(z.y) & 15) == 0) &&
+                         (!addr || ((z.ref_stride[3] == 1) && (z.ref_stride[2] == W) && (z.ref_stride[1] % 4 == 0) && (z.ref_stride[0] % 4 == 0) &&
+                                    ((reinterpret_cast<uintptr_t>(z.ref) & 15) == 0)));
+        const int et = tid - 64;
+        int k = 0;
+        for (int pt = first; pt < PT; pt += step, k++) {
+            const int n = pt / tiles, p0 = (pt % tiles) * 128;
+            const uint32_t buf = (uint32_t)k & 1u;
+            if (ew == 0) wait_bar(&bars[5 + buf], (uint32_t)(k >> 1) & 1u);
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (et == 0 && k < 8) ZTR(16 + k);
+            tc_fence_after();
+            const int pp = lane * 4, p = p0 + pp;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                if (h * HB < CO) {
+                    // residual rows of this half: issued first, consumed after the transposition
+                    float4 res[HB / 8];
+#pragma unroll
+                    for (int kk = 0; kk < HB / 8; kk++) {
+                        const int ol = h * HB + ew + 8 * kk;
+                        res[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (addr && vec && p + 3 < HW && ol < CO)
+                            res[kk] = __ldg(reinterpret_cast<const float4 *>(z.ref + (int64_t)n * z.ref_stride[0] + (int64_t)(oc0 + ol) * z.ref_stride[1] + p));
+                    }
+                    {
+                        // a warp reads the TMEM lane quadrant (warp index % 4); warps 2-5 take the first 32 columns of the half, 6-9 the rest
+                        const int r = (warp & 3) * 32 + lane, cb = (ew >> 2) * 32;
+                        float v[32];
+                        tmem_ld_32x32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + buf * NB + h * HB + cb, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int jj = 0; jj < 32; jj++) otile[(cb + jj) * OT + r] = v[jj];
+                    }
+                    if (h == 1 || HB >= CO) tc_fence_before();
+                    asm volatile("bar.sync 1, 256;" ::: "memory");
+                    if ((h == 1 || HB >= CO) && et == 0) mbar_arrive(&bars[7 + buf]);       // accumulator buffer drained
+#pragma unroll
+                    for (int kk = 0; kk < HB / 8; kk++) {
+                        const int hl = ew + 8 * kk, ol = h * HB + hl;
+                        if (ol < CO) {
+                            const int o = oc0 + ol;
+                            const float4 t = *reinterpret_cast<const float4 *>(otile + hl * OT + pp);
+                            const float b = bias[h][kk];
+                            float y[4] = {t.x + b, t.y + b, t.z + b, t.w + b};
+                            if (vec && p + 3 < HW) {
+                                *reinterpret_cast<float4 *>(z.y + (int64_t)n * z.y_stride[0] + (int64_t)o * z.y_stride[1] + p) =
+                                    make_float4(y[0] + res[kk].x, y[1] + res[kk].y, y[2] + res[kk].z, y[3] + res[kk].w);
+                            } else {
+                                for (int e = 0; e < 4 && p + e < HW; e++) {
+                                    const int py = (p + e) / W, px = (p + e) % W;
+                                    float val = y[e];
+                                    if (addr) val += __ldg(z.ref + (int64_t)n * z.ref_stride[0] + (int64_t)o * z.ref_stride[1] + (int64_t)py * z.ref_stride[2] + (int64_t)px * z.ref_stride[3]);
+                                    z.y[(int64_t)n * z.y_stride[0] + (int64_t)o * z.y_stride[1] + (int64_t)py * z.y_stride[2] + (int64_t)px * z.y_stride[3]] = val;
+                                }
+                            }
+                        }
+                    }
+                    asm volatile("bar.sync 1, 256;" ::: "memory");                          // the tile is rewritten by the next pass
+                }
+            }
+            if (et == 0 && k < 8) ZTR(24 + k);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc(tmem, 256);
+#ifdef EPI_PIPE_TIMERS
+    if (tid == 0) { ZTR(4); const unsigned long long g = gtime(); atomicMin(&g_zg_span[2], g); atomicMax(&g_zg_span[3], g); }
+#endif
+}
+
+#ifdef EPI_PIPE_TIMERS
+extern "C" void epi_zgemm_trace_read(long long *out64, unsigned long long *span4, int reset) {
+    cudaMemcpyFromSymbol(out64, g_zg_trace, sizeof(long long) * 64);
+    cudaMemcpyFromSymbol(span4, g_zg_span, sizeof(unsigned long long) * 4);
+    if (reset) { unsigned long long z4[4] = {~0ull, 0ull, ~0ull, 0ull}; cudaMemcpyToSymbol(g_zg_span, z4, sizeof(z4)); }
+}
+#endif
+
+bool zgemm_supported(int C) { return C % 64 == 0 && C >= 64 && C <= 512; }   // whole 64-channel TMA panels
 
 namespace {
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
@@ -193,23 +428,38 @@ bool make_plane_map(CUtensorMap *m, const __nv_bfloat16 *base, int rows, int C, 
 
 cudaError_t launch_zgemm(const ZGemmArgs &z, cudaStream_t st) {
     const int tiles = (z.HW + 127) / 128;
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(epi_zgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zg::SMEM_ALLOC);
+    const bool persist = z.C <= 256;
+    static thread_local bool attr_set[2] = {false, false};
+    if (!attr_set[persist ? 1 : 0]) {
+        cudaError_t e = persist ? cudaFuncSetAttribute(epi_zgemm_persist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zp::SMEM_ALLOC)
+                                : cudaFuncSetAttribute(epi_zgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)zg::SMEM_ALLOC);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        attr_set[persist ? 1 : 0] = true;
     }
     // tensor maps are a pure function of (pointers, shape): keep the last set per host thread
     struct MapCache { const void *xh, *wh; int rows, C; CUtensorMap m[4]; };
     static thread_local MapCache mc = {nullptr, nullptr, 0, 0, {}};
     if (mc.xh != z.x_hi || mc.wh != z.w_hi || mc.rows != z.N * z.HW || mc.C != z.C) {
-        const int wrows = z.C < 256 ? z.C : 256;
+        const int wrows = z.C < zg::NB ? z.C : zg::NB;
         if (!make_plane_map(&mc.m[0], z.x_hi, z.N * z.HW, z.C, 128) || !make_plane_map(&mc.m[1], z.x_lo, z.N * z.HW, z.C, 128) ||
             !make_plane_map(&mc.m[2], z.w_hi, z.C, z.C, wrows) || !make_plane_map(&mc.m[3], z.w_lo, z.C, z.C, wrows))
             return cudaErrorInvalidValue;
         mc.xh = z.x_hi; mc.wh = z.w_hi; mc.rows = z.N * z.HW; mc.C = z.C;
     }
-    return launch_pdl(epi_zgemm_kernel, dim3((unsigned)(z.N * tiles), (unsigned)((z.C + 255) / 256)), dim3(zg::NT), (size_t)zg::SMEM_ALLOC, st, z, mc.m[0], mc.m[1], mc.m[2], mc.m[3]);
+    if (persist) {
+        static thread_local int sms_cached = 0;
+        if (!sms_cached) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            if (cudaDeviceGetAttribute(&sms_cached, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms_cached <= 0) sms_cached = 148;
+        }
+        const int nblk = (z.C + zp::NB - 1) / zp::NB, PT = z.N * tiles;
+        int per = sms_cached / nblk;                       // CTAs per block of output channels
+        if (per > PT) per = PT;
+        if (per < 1) per = 1;
+        return launch_pdl(epi_zgemm_persist_kernel, dim3((unsigned)(per * nblk)), dim3(zp::NT), (size_t)zp::SMEM_ALLOC, st, z, mc.m[0], mc.m[1], mc.m[2], mc.m[3]);
+    }
+    return launch_pdl(epi_zgemm_kernel, dim3((unsigned)(z.N * tiles), (unsigned)((z.C + zg::NB - 1) / zg::NB)), dim3(zg::NT), (size_t)zg::SMEM_ALLOC, st, z, mc.m[0], mc.m[1], mc.m[2], mc.m[3]);
 }
 
 }  // namespace epi

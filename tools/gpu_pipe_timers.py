@@ -17,7 +17,10 @@ P1 = torch.from_numpy(P1.astype(np.float32)).cuda(); P2 = torch.from_numpy(P2.as
 wf = torch.randn(C, C, device="cuda") * 0.05; bf = torch.randn(C, device="cuda")
 buf = (ctypes.c_ulonglong * 32)()
 state = epi.FusionState() if "--nocache" not in sys.argv else None
+zt = (ctypes.c_longlong * 64)(); zs = (ctypes.c_ulonglong * 4)()
+lib.epi_zgemm_trace_read(zt, zs, 1)
 for it in range(3):
+    if it == 2: lib.epi_zgemm_trace_read(zt, zs, 1)
     epi.epipolar_fusion(f1, f2, P1, P2, K=K, correct_normalize=True, variant="pipe", z_folded=(wf, bf), z_residual=True, state=state)
     torch.cuda.synchronize()
     lib.epi_pipe_timers_read(buf, 1)
@@ -48,3 +51,13 @@ print("item " + " ".join("%11s" % e[:11] for e in ev))
 for j in range(8):
     if t[j, 0] == 0 and j > 0: break
     print("%4d " % j + " ".join("%11.1f" % ((t[j, e] - t0) / 1e3) if t[j, e] else "%11s" % "-" for e in range(10)))
+
+# ---- persistent z GEMM: CTA 0 timeline (cycles since kernel entry) and the spread of CTA start / end times (globaltimer) ----
+lib.epi_zgemm_trace_read(zt, zs, 0)
+z = np.array(list(zt), dtype=np.int64); t0 = z[0]
+f = lambda i: (z[i] - t0) / 1e3 if z[i] else float("nan")
+print("zgemm CTA 0 (kcycles): prologue done %.1f, after pdl_wait %.1f, W landed %.1f, exit %.1f" % (f(1), f(2), f(3), f(4)))
+for k in range(4):
+    if z[8 + k]: print("  unit %d: MMAs issued %.1f, epilogue start %.1f, epilogue end %.1f" % (k, f(8 + k), f(16 + k), f(24 + k)))
+sp = list(zs)
+print("zgemm CTA starts spread %.2f us, first start -> last end %.2f us, ends spread %.2f us" % ((sp[1] - sp[0]) / 1e3, (sp[3] - sp[0]) / 1e3, (sp[3] - sp[2]) / 1e3))
