@@ -68,6 +68,35 @@ def measured_peaks():
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
+def bind_near_gpu(torch, index):
+    """Pin this process to the CPUs local to GPU `index` (sysfs local_cpulist of its PCI function); returns what it did."""
+    info = {"previous": None, "cpus": None, "node": None}
+    try:
+        pr = torch.cuda.get_device_properties(index)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        base = "/sys/bus/pci/devices/" + bdf
+        cl = open(base + "/local_cpulist").read().strip()
+        cpus = set()
+        for part in cl.split(","):
+            if "-" in part:
+                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        prev = os.sched_getaffinity(0)
+        cpus &= prev
+        if cpus and cpus != prev:
+            os.sched_setaffinity(0, cpus)
+            info["previous"] = prev
+        info["cpus"] = len(cpus)
+        try:
+            info["node"] = int(open(base + "/numa_node").read().strip())
+        except (OSError, ValueError):
+            pass
+    except (OSError, AttributeError, ValueError, RuntimeError):
+        pass
+    return info
+
+
 def make_config(args, wl, world):
     """The `config` object: identical for both arms (the reference arm runs the same workload on the host CPU)."""
     N = wl["N"]
@@ -436,6 +465,9 @@ def run_ours(args, wl):
                  "exchange_and_host_ms": max(0.0, call_ms - float(g.sum())), "synchronised_call_ms": call_ms}
 
     # ---- end to end through the public module call with HOST buffers (pinned), copies inside the timed region ----
+    # The pinned buffers are allocated (and the copies driven) from the CPUs of the GPU's own NUMA node: host memory one socket
+    # away costs 20-40 % of the PCIe rate on these boxes (run-to-run spread of e2e before this: 0.71-1.27 ms/step).
+    numa = bind_near_gpu(torch, dev.index if dev.index is not None else 0)
     h_ref = [refs[i].cpu().pin_memory() for i in range(2)]
     h_src = [srcs[i].cpu().pin_memory() for i in range(2)] if world == 1 else None
     h_out = torch.empty((N, C, H, W), dtype=torch.float32).pin_memory()
@@ -491,6 +523,11 @@ def run_ours(args, wl):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item()) / e2e_steps
     clocks = sampler.stop() if sampler else None
+    if numa.get("previous") is not None:
+        try:
+            os.sched_setaffinity(0, numa["previous"])
+        except OSError:
+            pass
     h2d = (2 if world == 1 else 1) * N * C * H * W * 4 + (2 * N * 48 if world == 1 else 0)
     d2h = N * C * H * W * 4 + N * K * H * W * 4 + N * H * W * 8
 
@@ -511,7 +548,8 @@ def run_ours(args, wl):
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": cfgd, "clocks": clocks,
             "e2e": {"value": world * N / (e2e_ms * 1e-3), "unit": "views/s", "ms_per_step": e2e_ms, "wall_ms_per_step": wall_ms / e2e_steps,
-                    "how": e2e_how, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                    "how": e2e_how, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "host_numa": {"node": numa.get("node"), "cpus_bound": numa.get("cpus"), "rebound": numa.get("previous") is not None}},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "epi_fusion_pipe_kernel: fused epipolar attention (geometry + taps + softmax + AV)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

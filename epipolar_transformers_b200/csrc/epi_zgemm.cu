@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(zp::NT, 1) epi_zgemm_persist_kernel(const ZGem
     using namespace zp;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);     // [0] W landed, [1,2] A stage full, [3,4] A stage free, [5,6] accumulator full, [7,8] accumulator free
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + OFF_BAR);     // [0-3] W panel landed, [4,5] A stage full, [6,7] A stage free, [8,9] accumulator full, [10,11] accumulator free
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 128);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int C = z.C, HW = z.HW, W = z.W;
@@ -244,8 +244,7 @@ __global__ void __launch_bounds__(zp::NT, 1) epi_zgemm_persist_kernel(const ZGem
     }
     if (warp == 2) tmem_alloc(tmem_slot, 256);
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        for (int i = 0; i < 2; i++) { mbar_init(&bars[1 + i], 1); mbar_init(&bars[3 + i], 1); mbar_init(&bars[5 + i], 1); mbar_init(&bars[7 + i], 1); }
+        for (int i = 0; i < 12; i++) mbar_init(&bars[i], 1);
         mbar_fence_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_hi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tm_lo) : "memory");
@@ -264,38 +263,40 @@ __global__ void __launch_bounds__(zp::NT, 1) epi_zgemm_persist_kernel(const ZGem
         // ---------------- TMA producer ----------------
         if (lane == 0 && first < PT) {
             const uint32_t wrows = (uint32_t)(C < NB ? C : NB);
-            mbar_arrive_expect_tx(&bars[0], (uint32_t)nq * 2u * wrows * 128u);
-            for (int q = 0; q < nq; q++) {
-                zg::tma_load_2d(smem + OFF_W + q * W_PANEL, &tw_hi, q * 64, oc0, &bars[0]);
-                zg::tma_load_2d(smem + OFF_W + q * W_PANEL + W_PLANE, &tw_lo, q * 64, oc0, &bars[0]);
-            }
             uint32_t ac = 0;
+            bool first_unit = true;
             for (int pt = first; pt < PT; pt += step) {
                 const int n = pt / tiles, p0 = (pt % tiles) * 128;
                 for (int q = 0; q < nq; q++, ac++) {
+                    if (first_unit) {                         // weight panel q right before the first A panel that multiplies with it: one
+                        mbar_arrive_expect_tx(&bars[q], 2u * wrows * 128u);     // barrier per panel, so the MMAs start after 1/nq of the weight
+                        zg::tma_load_2d(smem + OFF_W + q * W_PANEL, &tw_hi, q * 64, oc0, &bars[q]);
+                        zg::tma_load_2d(smem + OFF_W + q * W_PANEL + W_PLANE, &tw_lo, q * 64, oc0, &bars[q]);
+                    }
                     const uint32_t s = ac & 1u;
-                    if (ac >= 2) wait_bar(&bars[3 + s], ((ac >> 1) - 1u) & 1u);
-                    mbar_arrive_expect_tx(&bars[1 + s], 2 * A_PLANE);
-                    zg::tma_load_2d(smem + OFF_A + s * A_STAGE, &tm_hi, q * 64, n * HW + p0, &bars[1 + s]);
-                    zg::tma_load_2d(smem + OFF_A + s * A_STAGE + A_PLANE, &tm_lo, q * 64, n * HW + p0, &bars[1 + s]);
+                    if (ac >= 2) wait_bar(&bars[6 + s], ((ac >> 1) - 1u) & 1u);
+                    mbar_arrive_expect_tx(&bars[4 + s], 2 * A_PLANE);
+                    zg::tma_load_2d(smem + OFF_A + s * A_STAGE, &tm_hi, q * 64, n * HW + p0, &bars[4 + s]);
+                    zg::tma_load_2d(smem + OFF_A + s * A_STAGE + A_PLANE, &tm_lo, q * 64, n * HW + p0, &bars[4 + s]);
                 }
+                first_unit = false;
             }
         }
     } else if (warp == 1) {
         // ---------------- MMA issuer ----------------
         if (lane == 0 && first < PT) {
             const uint32_t idesc = make_idesc_bf16(128, (uint32_t)((CO + 15) & ~15), 0, 0);
-            wait_bar(&bars[0], 0);
             ZTR(3);
             uint32_t ac = 0;
             int k = 0;
             for (int pt = first; pt < PT; pt += step, k++) {
                 const uint32_t buf = (uint32_t)k & 1u;
-                if (k >= 2) wait_bar(&bars[7 + buf], (uint32_t)((k >> 1) - 1) & 1u);
+                if (k >= 2) wait_bar(&bars[10 + buf], (uint32_t)((k >> 1) - 1) & 1u);
                 tc_fence_after();
                 for (int q = 0; q < nq; q++, ac++) {
                     const uint32_t s = ac & 1u;
-                    wait_bar(&bars[1 + s], (ac >> 1) & 1u);
+                    if (k == 0) wait_bar(&bars[q], 0);            // weight panel q (resident afterwards)
+                    wait_bar(&bars[4 + s], (ac >> 1) & 1u);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + OFF_A + s * A_STAGE), sb = smem_u32(smem + OFF_W + q * W_PANEL);
 #pragma unroll
@@ -306,9 +307,9 @@ __global__ void __launch_bounds__(zp::NT, 1) epi_zgemm_persist_kernel(const ZGem
                         mma_bf16(tmem + buf * NB, a_hi, b_lo, idesc, 1u);
                         mma_bf16(tmem + buf * NB, a_lo, b_hi, idesc, 1u);
                     }
-                    mma_commit(&bars[3 + s]);
+                    mma_commit(&bars[6 + s]);
                 }
-                mma_commit(&bars[5 + buf]);
+                mma_commit(&bars[8 + buf]);
                 if (k < 8) ZTR(8 + k);
             }
         }
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(zp::NT, 1) epi_zgemm_persist_kernel(const ZGem
         for (int pt = first; pt < PT; pt += step, k++) {
             const int n = pt / tiles, p0 = (pt % tiles) * 128;
             const uint32_t buf = (uint32_t)k & 1u;
-            if (ew == 0) wait_bar(&bars[5 + buf], (uint32_t)(k >> 1) & 1u);
+            if (ew == 0) wait_bar(&bars[8 + buf], (uint32_t)(k >> 1) & 1u);
             asm volatile("bar.sync 1, 256;" ::: "memory");
             if (et == 0 && k < 8) ZTR(16 + k);
             tc_fence_after();
@@ -353,7 +354,7 @@ __global__ void __launch_bounds__(zp::NT, 1) epi_zgemm_persist_kernel(const ZGem
                     }
                     if (h == 1 || HB >= CO) tc_fence_before();
                     asm volatile("bar.sync 1, 256;" ::: "memory");
-                    if ((h == 1 || HB >= CO) && et == 0) mbar_arrive(&bars[7 + buf]);       // accumulator buffer drained
+                    if ((h == 1 || HB >= CO) && et == 0) mbar_arrive(&bars[10 + buf]);       // accumulator buffer drained
 #pragma unroll
                     for (int kk = 0; kk < HB / 8; kk++) {
                         const int hl = ew + 8 * kk, ol = h * HB + hl;

@@ -93,6 +93,9 @@ int main() {
     run_case(2, 64, 32, 32, 32, 1, EPI_VARIANT_AUTO);
     run_case(1, 256, 64, 64, 64, 1, EPI_VARIANT_AUTO);
     run_case(1, 40, 12, 20, 16, 0, EPI_VARIANT_AUTO);       // C % 64 != 0, ragged map
+    run_case(1, 512, 24, 24, 32, 1, EPI_VARIANT_PIPE);      // wide: two query-panel halves, single-buffered O, one-tile-per-CTA z GEMM
+    run_case(1, 320, 16, 24, 16, 0, EPI_VARIANT_PIPE);      // wide, C % 128 != 0, pixel-major plane + transposition pass
+    run_case(1, 16, 136, 136, 16, 0, EPI_VARIANT_PIPE);     // > 16384 pixels: row-windowed union bitmap, pixel order in its own launch
     run_case(1, 24, 16, 16, 16, 0, EPI_VARIANT_WARP);
     run_case(1, 32, 16, 16, 16, 0, EPI_VARIANT_SECTOR);
     // peak finder
