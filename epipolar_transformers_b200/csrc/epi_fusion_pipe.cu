@@ -150,6 +150,7 @@ using namespace pipe;
 #ifdef EPI_PIPE_TIMERS
 __device__ unsigned long long g_pipe_timers[32];
 __device__ long long g_pipe_trace[64 * 16];
+__device__ unsigned long long g_pipe_cta[256 * 4];     // per CTA: globaltimer at entry, after the dependency wait, at exit; items processed
 #define TR(item, ev) do { if (blockIdx.x == 0 && (item) < 64) g_pipe_trace[(item) * 16 + (ev)] = clock64(); } while (0)
 #define PT_DECL long long pt_prev = clock64()
 #define PT(slot) do { if (pt_on) { const long long t_ = clock64(); atomicAdd(&g_pipe_timers[slot], (unsigned long long)(t_ - pt_prev)); pt_prev = t_; } } while (0)
@@ -191,6 +192,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
 
     // ---------------- one-time setup (overlaps the staging launch's tail: programmatic dependent launch) ----------------
     pdl_launch_dependents();
+#ifdef EPI_PIPE_TIMERS
+    if (tid == 0 && blockIdx.x < 256) { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); g_pipe_cta[blockIdx.x * 4] = g; }
+#endif
     if (warp == 0) tmem_alloc(&ct.tmem_base, TMEM_COLS);
     if (tid == 32) {
         for (int i = 0; i < NDESC; i++) { mbar_init(&ct.desc_full[i], 1); mbar_init(&ct.desc_free[i], 2); }
@@ -209,6 +213,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
     tc_fence_after();
     const uint32_t tmem = ct.tmem_base;
     pdl_wait();                                     // operand planes, pixel order, pair constants, counters: the staging launch
+#ifdef EPI_PIPE_TIMERS
+    if (tid == 0 && blockIdx.x < 256) { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); g_pipe_cta[blockIdx.x * 4 + 1] = g; }
+#endif
 
     if (warp < NWORK) {
         // =====================================================================================================
@@ -303,6 +310,9 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
             if (tid == 0 && j >= 2) mbar_arrive(&ct.desc_free[(j - 2) % NDESC]);
             const Desc &d = desc_at(j);
             PT(1);
+#ifdef EPI_PIPE_TIMERS
+            if (d.tile < 0 && tid == 0 && blockIdx.x < 256) g_pipe_cta[blockIdx.x * 4 + 3] = (unsigned long long)j;
+#endif
             if (d.tile < 0) break;
             const int D = d.D, n = d.n;
             const int nch = (D + CHUNK - 1) / CHUNK;
@@ -455,7 +465,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                 const int k = warp + NWORK * jj;
                 if (act && k < K) {
                     const float av = x[jj] * inv;
-                    if (ab) ab[(size_t)k * HW] = av;
+                    if (ab) __stcs(ab + (size_t)k * HW, av);          // outputs are written once and not re-read here: streaming stores keep L2 for the planes
                     if (av > best_v) { best_v = av; best_k = k; }
                     // deterministic fixed-point scatter of a_k·w_kt into β[rank][pixel]
 #pragma unroll
@@ -486,7 +496,7 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
                     const float t = (float)bk / (float)(K - 1);
                     gx = img2grid_x(lerp_exact(en.x, en.z, t), gc); gy = img2grid_y(lerp_exact(en.y, en.w, t), gc);
                 }
-                reinterpret_cast<float2 *>(a.corr_pos)[(size_t)n * HW + pofs] = make_float2(grid2corr(gx, W, gc.correct), grid2corr(gy, H, gc.correct));
+                __stcs(reinterpret_cast<float2 *>(a.corr_pos) + (size_t)n * HW + pofs, make_float2(grid2corr(gx, W, gc.correct), grid2corr(gy, H, gc.correct)));
             }
             // ---------------- β[rank][pixel] -> bf16 (hi, lo) stacked K-major panels; warp <-> 16 ranks, lane <-> pixel ----------------
             PT(6);
@@ -1003,10 +1013,14 @@ __global__ void __launch_bounds__(NT_ALL, 1) epi_fusion_pipe_kernel(const Fusion
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, TMEM_COLS);
+#ifdef EPI_PIPE_TIMERS
+    if (tid == 0 && blockIdx.x < 256) { unsigned long long g; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(g)); g_pipe_cta[blockIdx.x * 4 + 2] = g; }
+#endif
 }
 
 
 #ifdef EPI_PIPE_TIMERS
+extern "C" void epi_pipe_cta_read(unsigned long long *out1024) { cudaMemcpyFromSymbol(out1024, g_pipe_cta, sizeof(unsigned long long) * 1024); }
 extern "C" void epi_pipe_trace_read(long long *out1024) { cudaMemcpyFromSymbol(out1024, g_pipe_trace, sizeof(long long) * 64 * 16); }
 extern "C" void epi_pipe_timers_read(unsigned long long *out32, int reset) {
     cudaMemcpyFromSymbol(out32, g_pipe_timers, sizeof(unsigned long long) * 32);

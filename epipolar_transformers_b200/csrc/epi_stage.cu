@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(stg::NT, 5) epi_stage_kernel(const StageArgs s
     const int fq = t & 15, hsel = (t >> 4) & 1, fw = t >> 5;
     auto fast_load = [&](const float *spn, int64_t scn, int c0n, int p0n, float4 *v) {
 #pragma unroll
-        for (int i = 0; i < RPASS; i++) v[i] = __ldg(reinterpret_cast<const float4 *>(spn + (int64_t)(c0n + 2 * fw + hsel + i * RPP) * scn + p0n + fq * 4));
+        for (int i = 0; i < RPASS; i++) v[i] = __ldcs(reinterpret_cast<const float4 *>(spn + (int64_t)(c0n + 2 * fw + hsel + i * RPP) * scn + p0n + fq * 4));   // read once: streaming, keeps L2 for the planes
     };
     auto fast_split = [&](const float4 *v) {            // registers -> (hi, lo) words in shared memory
 #pragma unroll

@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(zg::NT, 2) epi_zgemm_kernel(const ZGemmArgs z,
             res[k] = make_float4(0.f, 0.f, 0.f, 0.f);
             bias[k] = ol < CO ? __ldg(z.bf + oc0 + ol) : 0.f;      // folded bias: written long before the staging launch
             if (addr && vec && p + 3 < HW && ol < CO)
-                res[k] = __ldg(reinterpret_cast<const float4 *>(z.ref + (int64_t)n * z.ref_stride[0] + (int64_t)(oc0 + ol) * z.ref_stride[1] + p));
+                res[k] = __ldcs(reinterpret_cast<const float4 *>(z.ref + (int64_t)n * z.ref_stride[0] + (int64_t)(oc0 + ol) * z.ref_stride[1] + p));
         }
     }
     if (warp == 0) tmem_alloc(tmem_slot, NB);
@@ -157,8 +157,8 @@ __global__ void __launch_bounds__(zg::NT, 2) epi_zgemm_kernel(const ZGemmArgs z,
             const float b = bias[k];
             float y[4] = {t.x + b, t.y + b, t.z + b, t.w + b};
             if (vec && p + 3 < HW) {
-                *reinterpret_cast<float4 *>(z.y + (int64_t)n * z.y_stride[0] + (int64_t)o * z.y_stride[1] + p) =
-                    make_float4(y[0] + res[k].x, y[1] + res[k].y, y[2] + res[k].z, y[3] + res[k].w);
+                __stcs(reinterpret_cast<float4 *>(z.y + (int64_t)n * z.y_stride[0] + (int64_t)o * z.y_stride[1] + p),     // written once, read by
+                       make_float4(y[0] + res[k].x, y[1] + res[k].y, y[2] + res[k].z, y[3] + res[k].w));               // nobody here: streaming
             } else {
                 for (int e = 0; e < 4 && p + e < HW; e++) {
                     const int py = (p + e) / W, px = (p + e) % W;
@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(zp::NT, 1) epi_zgemm_persist_kernel(const ZGem
                         const int ol = h * HB + ew + 8 * kk;
                         res[kk] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (addr && vec && p + 3 < HW && ol < CO)
-                            res[kk] = __ldg(reinterpret_cast<const float4 *>(z.ref + (int64_t)n * z.ref_stride[0] + (int64_t)(oc0 + ol) * z.ref_stride[1] + p));
+                            res[kk] = __ldcs(reinterpret_cast<const float4 *>(z.ref + (int64_t)n * z.ref_stride[0] + (int64_t)(oc0 + ol) * z.ref_stride[1] + p));
                     }
                     {
                         // a warp reads the TMEM lane quadrant (warp index % 4); warps 2-5 take the first 32 columns of the half, 6-9 the rest
@@ -364,8 +364,8 @@ __global__ void __launch_bounds__(zp::NT, 1) epi_zgemm_persist_kernel(const ZGem
                             const float b = bias[h][kk];
                             float y[4] = {t.x + b, t.y + b, t.z + b, t.w + b};
                             if (vec && p + 3 < HW) {
-                                *reinterpret_cast<float4 *>(z.y + (int64_t)n * z.y_stride[0] + (int64_t)o * z.y_stride[1] + p) =
-                                    make_float4(y[0] + res[kk].x, y[1] + res[kk].y, y[2] + res[kk].z, y[3] + res[kk].w);
+                                __stcs(reinterpret_cast<float4 *>(z.y + (int64_t)n * z.y_stride[0] + (int64_t)o * z.y_stride[1] + p),   // streaming: written
+                                       make_float4(y[0] + res[kk].x, y[1] + res[kk].y, y[2] + res[kk].z, y[3] + res[kk].w));           // once, not re-read here
                             } else {
                                 for (int e = 0; e < 4 && p + e < HW; e++) {
                                     const int py = (p + e) / W, px = (p + e) % W;

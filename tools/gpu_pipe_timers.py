@@ -61,3 +61,14 @@ for k in range(4):
     if z[8 + k]: print("  unit %d: MMAs issued %.1f, epilogue start %.1f, epilogue end %.1f" % (k, f(8 + k), f(16 + k), f(24 + k)))
 sp = list(zs)
 print("zgemm CTA starts spread %.2f us, first start -> last end %.2f us, ends spread %.2f us" % ((sp[1] - sp[0]) / 1e3, (sp[3] - sp[0]) / 1e3, (sp[3] - sp[2]) / 1e3))
+
+# ---- fused kernel: per-CTA start / end (globaltimer) and item counts: where the tail comes from ----
+cb = (ctypes.c_ulonglong * 1024)()
+lib.epi_pipe_cta_read(cb)
+c = np.array(list(cb), dtype=np.float64).reshape(256, 4)[:148]
+t0 = c[:, 0].min()
+ent, dep, end, items = (c[:, 0] - t0) / 1e3, (c[:, 1] - t0) / 1e3, (c[:, 2] - t0) / 1e3, c[:, 3]
+print("fused kernel CTAs: entry spread %.2f us, dependency wait ends %.2f..%.2f us, exits %.2f..%.2f us (median %.2f)" % (ent.max(), dep.min(), dep.max(), end.min(), end.max(), np.median(end)))
+for n in sorted(set(items.astype(int))):
+    m = items == n
+    print("  %d CTAs with %d items: exit %.2f..%.2f us (mean %.2f)" % (m.sum(), n, end[m].min(), end[m].max(), end[m].mean()))
