@@ -68,35 +68,6 @@ def measured_peaks():
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
-def bind_near_gpu(torch, index):
-    """Pin this process to the CPUs local to GPU `index` (sysfs local_cpulist of its PCI function); returns what it did."""
-    info = {"previous": None, "cpus": None, "node": None}
-    try:
-        pr = torch.cuda.get_device_properties(index)
-        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
-        base = "/sys/bus/pci/devices/" + bdf
-        cl = open(base + "/local_cpulist").read().strip()
-        cpus = set()
-        for part in cl.split(","):
-            if "-" in part:
-                a, b = part.split("-"); cpus.update(range(int(a), int(b) + 1))
-            elif part:
-                cpus.add(int(part))
-        prev = os.sched_getaffinity(0)
-        cpus &= prev
-        if cpus and cpus != prev:
-            os.sched_setaffinity(0, cpus)
-            info["previous"] = prev
-        info["cpus"] = len(cpus)
-        try:
-            info["node"] = int(open(base + "/numa_node").read().strip())
-        except (OSError, ValueError):
-            pass
-    except (OSError, AttributeError, ValueError, RuntimeError):
-        pass
-    return info
-
-
 def make_config(args, wl, world):
     """The `config` object: identical for both arms (the reference arm runs the same workload on the host CPU)."""
     N = wl["N"]
@@ -467,7 +438,7 @@ def run_ours(args, wl):
     # ---- end to end through the public module call with HOST buffers (pinned), copies inside the timed region ----
     # The pinned buffers are allocated (and the copies driven) from the CPUs of the GPU's own NUMA node: host memory one socket
     # away costs 20-40 % of the PCIe rate on these boxes (run-to-run spread of e2e before this: 0.71-1.27 ms/step).
-    numa = bind_near_gpu(torch, dev.index if dev.index is not None else 0)
+    numa = epi.bind_host_to_gpu(dev.index if dev.index is not None else 0)
     h_ref = [refs[i].cpu().pin_memory() for i in range(2)]
     h_src = [srcs[i].cpu().pin_memory() for i in range(2)] if world == 1 else None
     h_out = torch.empty((N, C, H, W), dtype=torch.float32).pin_memory()

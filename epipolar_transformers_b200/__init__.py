@@ -11,10 +11,10 @@ and fails loudly if the library is missing.
 """
 from .config import Node, default_cfg, make_cfg, get_global_cfg, set_global_cfg, cfg_h36m_r50_256, cfg_h36m_r152_384
 from .epipolar import Epipolar, FusionState, ZeroInitBN, epipolar_fusion, fold_z_bn, sample_locs, fused_other_feat
-from .host_pipeline import HostStreamer
+from .host_pipeline import HostStreamer, bind_host_to_gpu
 from .peaks import find_tensor_peak_batch
 from . import multiview, synthetic
 
-__all__ = ["Epipolar", "FusionState", "HostStreamer", "ZeroInitBN", "epipolar_fusion", "fold_z_bn", "sample_locs", "fused_other_feat", "find_tensor_peak_batch",
+__all__ = ["Epipolar", "FusionState", "HostStreamer", "bind_host_to_gpu", "ZeroInitBN", "epipolar_fusion", "fold_z_bn", "sample_locs", "fused_other_feat", "find_tensor_peak_batch",
            "Node", "default_cfg", "make_cfg", "get_global_cfg", "set_global_cfg",
            "cfg_h36m_r50_256", "cfg_h36m_r152_384", "multiview", "synthetic"]

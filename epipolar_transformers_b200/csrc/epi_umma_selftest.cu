@@ -88,6 +88,9 @@ extern "C" int epi_umma_selftest(int mode, const float *A, const float *B, float
     return cudaGetLastError() == cudaSuccess ? EPI_OK : EPI_ECUDA;
 }
 
+// The micro-benchmark and the M=64 probe below are developer tools: they are compiled into libepipolar_b200_timers.so only
+// (`python -m epipolar_transformers_b200.build --timers`), never into the product library.
+#ifdef EPI_PIPE_TIMERS
 // ---- micro-benchmark: cycles per tcgen05.mma for M=128, K=16 bf16, N in {32..256}, A K-major or MN-major ----
 namespace epi {
 using namespace umma;
@@ -199,3 +202,4 @@ extern "C" int epi_umma_m64_probe(int mn_major, const float *A, const float *B, 
     epi::umma_m64_probe_kernel<<<1, 128, smem, reinterpret_cast<cudaStream_t>(stream)>>>(mn_major, A, B, Dall, N, K);
     return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
+#endif  // EPI_PIPE_TIMERS

@@ -3,6 +3,7 @@ import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from epipolar_transformers_b200 import _lib
+_lib.LIB_PATH = os.path.join(os.path.dirname(_lib.LIB_PATH), "libepipolar_b200_timers.so")   # developer build (build.py --timers)
 lib = _lib.load()
 for mn in (0, 1):
     N, K = 32, 128
