@@ -98,6 +98,33 @@ def test_workspace_plan(lib):
     assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == m             # warp kernel reads channels_last in place
 
 
+def test_kernel_selection_by_shape(lib):
+    """Shape limits of the pipelined kernel as the ABI applies them (no GPU call): `epi_fusion_cache_bytes` is non-zero exactly
+    when that kernel is selected (it is the only one that keeps cross-call state)."""
+    def cache(C, H, W, K, variant=_lib.EPI_VARIANT_AUTO, N=2):
+        p = _lib.EpiFusionParams()
+        p.N, p.C, p.H, p.W, p.K = N, C, H, W, K
+        p.variant = variant
+        return lib.epi_fusion_cache_bytes(ctypes.byref(p))
+    assert cache(256, 64, 64, 64) > 0                       # BASELINE config 2
+    assert cache(512, 64, 64, 128) > 0                      # wide: two query-panel halves; K = 128 fits because 4*max(H, W) = 256
+    assert cache(520, 64, 64, 64) == 0                      # C > 512
+    assert cache(260, 64, 64, 64) == 0                      # C % 8 != 0
+    assert cache(64, 256, 256, 32) > 0                      # 65536 pixels: row-windowed union bitmap
+    assert cache(64, 100, 400, 48) > 0                      # non-square above 16384 pixels
+    assert cache(64, 300, 100, 16) == 0                     # more than 256 rows
+    assert cache(64, 128, 128, 128) == 0                    # a single pixel's union (min(4K, 4*max)) exceeds 256 rows
+    # automatic selection leaves K > 48 on maps of 2K+ pixels a side to the other kernels; forcing the kernel still works
+    assert cache(256, 128, 128, 64) == 0 and cache(256, 256, 256, 64) == 0
+    assert cache(256, 128, 128, 64, _lib.EPI_VARIANT_PIPE) > 0 and cache(256, 96, 96, 64) > 0 and cache(256, 256, 256, 48) > 0
+    # workspace of the wide / large-map plans: operand planes + counters (+ order, pair constants without a cache)
+    p = _lib.EpiFusionParams()
+    p.N, p.C, p.H, p.W, p.K = 1, 512, 32, 32, 64
+    p.out_stride = (ctypes.c_int64 * 4)(512 * 1024, 1, 32 * 512, 512)       # channels_last output
+    m = 512 * 1024 * 4
+    assert lib.epi_fusion_workspace_bytes(ctypes.byref(p)) == 2 * m + 256 + 1024 * 2 + 256
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
